@@ -1,0 +1,155 @@
+/* libvda — C ABI of the B200-native Video-Depth-Anything hot path.
+ *
+ * The reference has no FFI: its boundary is the Python nn.Module surface
+ * (video_depth_anything/video_depth.py:38-63 ctor, :89-164 forward, :166-254 infer_video_depth).
+ * Everything those functions delegate to torch.nn / ATen operators is replaced by the entry points
+ * below (one per operator family); the Python mirror in video_depth_anything_b200/ binds them with
+ * ctypes.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error (message: vda_last_error()).
+ *   - all pointers are DEVICE pointers unless named host_*; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*), no hidden synchronisation.
+ *   - "h16" tensors hold 16-bit floats: bf16 when dtype == VDA_BF16, fp16 when VDA_FP16.
+ *   - activations are token-major / NHWC:  [frames, h*w, C].
+ */
+#ifndef VDA_H_
+#define VDA_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { VDA_BF16 = 0, VDA_FP16 = 1 };
+enum { VDA_OUT_H16 = 0, VDA_OUT_F32 = 1 };
+enum { VDA_ACT_NONE = 0, VDA_ACT_GELU = 1, VDA_ACT_RELU = 2 };
+
+/* epilogue families of the tensor-core GEMM */
+enum {
+  VDA_EPI_LINEAR = 0, /* bias, layer-scale, activation, up to two residuals, optional relu'd copy        */
+  VDA_EPI_GEGLU = 1,  /* out[m,j] = (a+ba) * gelu(g+bg); weight rows interleaved per 2*geglu_half block  */
+  VDA_EPI_CONVT = 2,  /* ConvTranspose2d with kernel == stride: pixel-shuffle scatter store              */
+  VDA_EPI_TAIL = 3    /* relu(acc+bias) . w2 + b2 -> relu -> fp32 scalar per row (output_conv2)          */
+};
+
+/* A-operand addressing */
+enum {
+  VDA_A_PLAIN = 0,  /* A is a row-major [M,K] h16 matrix with row stride lda                            */
+  VDA_A_CONV3 = 1   /* implicit 3x3 / stride 1 / pad 1 convolution over an NHWC h16 tensor              */
+};
+
+typedef struct vda_gemm_params {
+  /* problem: out[M,N] = A[M,K] . Wt[N,K]^T  (both K-major, h16), fp32 accumulation in TMEM */
+  int32_t M, N, K;
+  int32_t dtype;    /* VDA_BF16 | VDA_FP16 */
+  int32_t a_mode;   /* VDA_A_PLAIN | VDA_A_CONV3 */
+  int32_t epilogue; /* VDA_EPI_* */
+  const void* A;    /* plain: [M,lda]; conv: NHWC [n_img,H,W,C] (C % 64 == 0, K == 9*C)        */
+  int64_t lda;
+  const void* Wt;   /* [N,K] row-major (nn.Linear layout); conv: K index = (ky*3+kx)*C + ci     */
+  int32_t n_img, H, W, C;
+
+  /* LINEAR epilogue: v = acc + bias[n]; v *= gamma[n]; v = act(v); v += res1[r,n]; v += res2[r,n] */
+  const float* bias;   /* [N] or NULL */
+  const float* gamma;  /* [N] or NULL (LayerScale, dinov2_layers/layer_scale.py:27-28) */
+  int32_t act;         /* VDA_ACT_* */
+  const void* res1;    /* NULL, or [rows,ldr1] fp32 (res1_f32 != 0) / h16 */
+  int64_t ldr1;
+  int32_t res1_f32;
+  const void* res2;    /* NULL or h16 [rows,ldo] */
+  void* out;           /* [rows,ldo] h16 or fp32 (out_f32) */
+  int64_t ldo;
+  int32_t out_f32;
+  void* out_relu;      /* NULL or h16 [rows,ldo]: relu(v), the pre-activated copy an RCU conv1 consumes */
+  /* row remap for the patch-embed GEMM (dinov2.py:212-219): with group = patches per frame,
+     out row = m + m/group + 1 (skips each frame's cls row) and res1 row = m % group + 1 (pos_embed). */
+  int32_t row_group;   /* 0 = identity mapping */
+
+  /* GEGLU: N is the packed width (2*inner); out has N/2 columns */
+  int32_t geglu_half;  /* columns of `a` per interleaved block (block = [a(half) | g(half)]) */
+
+  /* CONVT: rows are input pixels (img,y,x) of an in_h x in_w map; column j = (ky*S+kx)*Co + co */
+  int32_t convt_s, convt_co, in_h, in_w;
+
+  /* TAIL: N == 32; out is fp32 [rows] */
+  const float* tail_w; /* [32] */
+  float tail_b;
+} vda_gemm_params;
+
+int vda_version(void);
+const char* vda_last_error(void);
+/* fills sm count and compute capability of `device`; returns non-zero if it is not sm_100 */
+int vda_device_query(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* tcgen05/TMEM/TMA GEMM + implicit-GEMM conv (replaces nn.Linear / nn.Conv2d / nn.ConvTranspose2d call sites:
+ * dinov2_layers/attention.py:44-46, mlp.py:30-32, patch_embed.py:66, dpt.py:60-90,117-124, util/blocks.py:20-32,52-58,
+ * 124-126, motion_module/motion_module.py:85,100, motion_module/attention.py:81-83,90,335-338,382-384) */
+int vda_gemm(const vda_gemm_params* p, void* stream);
+
+/* nn.LayerNorm over the last dim (block.py:56,68; dinov2.py:165,309-310; motion_module.py:156-163).
+ * in: fp32 (in_f32) or h16 [rows, C]; out: h16 [rows_out, C].
+ * drop_group > 0: input rows are frames of drop_group tokens whose first (cls) token is dropped
+ * (dinov2.py:312), out row = r - r/drop_group - 1.
+ * pe != NULL: adds pe[(r / pe_rows_per_frame) % pe_frames, :] after the affine (PositionalEncoding,
+ * motion_module.py:196-198, applied to the normed states at :234-235). */
+int vda_layernorm(const void* in, int in_f32, void* out, const float* w, const float* b, float eps, int64_t rows,
+                  int C, int dtype, int drop_group, const float* pe, int pe_rows_per_frame, int pe_frames,
+                  void* stream);
+
+/* GroupNorm(32, C, eps) per frame over an NHWC h16 tensor [frames, hw, C] (motion_module.py:84,110).
+ * stats: fp32 scratch [frames*groups*2]. */
+int vda_groupnorm(const void* in, void* out, const float* w, const float* b, float eps, int frames, int hw, int C,
+                  int groups, float* stats, int dtype, void* stream);
+
+/* fused softmax(q k^T / sqrt(64)) v for the spatial ViT attention (dinov2_layers/attention.py:49-62).
+ * qkv: h16 [frames, N, 3, heads, 64] (the qkv Linear's output), out: h16 [frames, N, heads*64]. */
+int vda_attention_spatial(const void* qkv, void* out, int frames, int N, int heads, int dtype, void* stream);
+
+/* temporal attention core over the frame axis at every spatial position (motion_module.py:230-297 with
+ * motion_module/attention.py:182-211).  qkv: h16 [T*hw, 3*C] rows ordered (frame, position), columns
+ * [q | k | v], each split in `heads` heads of C/heads.  out: h16 [T*hw, C]. */
+int vda_attention_temporal(const void* qkv, void* out, int T, int hw, int C, int heads, int dtype, void* stream);
+
+/* im2col of the 14x14/14 patch-embed conv (patch_embed.py:66,76): x fp32 [frames,3,H,W] ->
+ * A h16 [frames*hp*wp, kpad], column = c*196 + ky*14 + kx, zero padded to kpad. */
+int vda_patch_im2col(const float* x, void* A, int frames, int H, int W, int kpad, int dtype, void* stream);
+
+/* tokens[f, 0, :] = cls_token + pos_embed[0]   (dinov2.py:218-219); tokens fp32 [frames, tokens_per_frame, D] */
+int vda_write_cls(float* tokens, const float* cls_token, const float* pos, int frames, int tokens_per_frame, int D,
+                  void* stream);
+
+/* bicubic pos-embed resampling (dinov2.py:179-210; A=-0.75, src=(dst+0.5)/scale-0.5, clamped taps).
+ * pos_in fp32 [1+S*S, D] -> pos_out fp32 [1+hp*wp, D] */
+int vda_pos_embed_bicubic(const float* pos_in, float* pos_out, int S, int hp, int wp, int D, void* stream);
+
+/* im2col of a 3x3 / stride 2 / pad 1 conv over NHWC h16 (dpt.py:84-89): out [n*oh*ow, 9*C] */
+int vda_im2col3x3_s2(const void* in, void* out, int n, int H, int W, int C, int dtype, void* stream);
+
+/* bilinear, align_corners=True, NHWC h16 [n,ih,iw,C] -> [n,oh,ow,C] (util/blocks.py:156-158, dpt_temporal.py:94-96) */
+int vda_bilinear_nhwc(const void* in, void* out, int n, int ih, int iw, int oh, int ow, int C, int dtype,
+                      void* stream);
+
+/* bilinear, align_corners=True, single-channel fp32 [n,ih,iw] -> [n,oh,ow] (video_depth.py:162,208) */
+int vda_bilinear_f32(const float* in, float* out, int n, int ih, int iw, int oh, int ow, void* stream);
+
+/* h16 elementwise: out = a + b (either may alias out) */
+int vda_add_h16(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+
+/* Key-frame least squares (utils/util.py:40-62 with the all-ones mask of video_depth.py:230-232).
+ * pred/target: fp32 [n] (two frames each).  scale_shift: fp32 [2] <- (s, t); identity if det == 0.
+ * scratch: double [5] workspace. */
+int vda_lsq_scale_shift(const float* pred, const float* target, int64_t n, float* scale_shift, double* scratch,
+                        void* stream);
+
+/* out = max(0, s*x + t) with (s,t) read from device memory; if blend_w != NULL (fp32 [frames]) then
+ * out[f] = prev[f]*(1-w[f]) + max(0, s*x[f]+t)*w[f]  (video_depth.py:234-250, utils/util.py:65-74).
+ * x, prev, out: fp32 [frames, hw]. */
+int vda_affine_clamp_blend(const float* x, const float* scale_shift, const float* prev, const float* blend_w,
+                           float* out, int frames, int64_t hw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDA_H_ */

@@ -1,0 +1,73 @@
+"""GPU parity of VideoDepthAnything.forward / infer_video_depth (through the C ABI) against
+  (a) the reference's own outputs committed under tests/golden/ and
+  (b) the oracle restatement on the same seeded inputs,
+with the tolerance of BASELINE.json's north_star: per-pixel relative depth error <= 1e-2, measured as
+|d - ref| / max(|ref|, 1e-3 max|ref|)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from e2e_checks import GOLD, build_model, golden_case, stage_report  # noqa: E402
+from oracle import vda_oracle as O  # noqa: E402
+
+TOL = 1e-2
+MAN = json.load(open(os.path.join(GOLD, "MANIFEST.json")))["cases"]
+FWD = [k for k, v in MAN.items() if v["kind"] == "forward"]
+IVD = [k for k, v in MAN.items() if v["kind"] == "infer_video_depth"]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("name", FWD)
+def test_forward_vs_reference_golden(name, dtype):
+    (mx, p999, mean), d = golden_case(name, dtype)
+    assert (d > 0).float().mean() > 0.99
+    assert mx <= TOL, f"{name} {dtype}: rel err max {mx:.3e} p99.9 {p999:.3e} mean {mean:.3e}"
+
+
+@pytest.mark.parametrize("name", IVD)
+def test_infer_video_depth_vs_reference_golden(name):
+    c = MAN[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    m, _ = build_model(c["encoder"], c["seed"], torch.float16)
+    m.metric = c["mode"] == "identity"
+    out, fps = m.infer_video_depth(g["frames"], 24, input_size=c["input_size"], device="cuda")
+    assert fps == 24 and out.shape == g["depth"].shape and out.dtype == np.float32
+    mx, p999, mean = O.rel_err(torch.from_numpy(out), torch.from_numpy(g["depth"]))
+    assert mx <= TOL, f"{name}: rel err max {mx:.3e} p99.9 {p999:.3e} mean {mean:.3e}"
+
+
+def test_forward_frame_permutation_sensitivity():
+    """The temporal path is live: permuting input frames changes outputs by far more than the tolerance."""
+    m, _ = build_model("vits", 0, torch.bfloat16)
+    x = torch.randn(1, 8, 3, 56, 70, generator=torch.Generator().manual_seed(1234)).cuda()
+    perm = torch.randperm(8, generator=torch.Generator().manual_seed(7))
+    d = m.forward(x)
+    dp = m.forward(x[:, perm.cuda()])
+    mx, _, _ = O.rel_err(dp[:, torch.argsort(perm).cuda()].cpu(), d.cpu())
+    assert mx > 3e-2
+
+
+def test_forward_is_deterministic_and_pure():
+    m, _ = build_model("vits", 0, torch.bfloat16)
+    x = torch.randn(1, 4, 3, 42, 56, generator=torch.Generator().manual_seed(3)).cuda()
+    x0 = x.clone()
+    a = m.forward(x)
+    b = m.forward(x)
+    assert torch.equal(a, b) and torch.equal(x, x0) and a.dtype == torch.float32 and (a >= 0).all()
+
+
+def test_forward_rejects_bad_shapes():
+    m, _ = build_model("vits", 0, torch.bfloat16)
+    with pytest.raises(AssertionError):
+        m.forward(torch.zeros(1, 2, 3, 50, 56).cuda())
+
+
+def test_stagewise_vs_oracle_vits():
+    fin, rows, d, ref = stage_report("vits", 0, (1, 8, 3, 56, 70), 1234, torch.float16)
+    worst = max(r[1] for r in rows)
+    assert fin[0] <= TOL and worst < 0.15, (fin, rows)

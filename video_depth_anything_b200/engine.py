@@ -1,0 +1,379 @@
+"""Host-side engine: packs a reference state dict (SURVEY.md App. C key set) into the layouts the sm_100a
+kernels want and sequences the kernels of one forward pass.
+
+Layout rules
+  * activations are token-major / NHWC h16 (`[frames, h*w, C]`), so none of the reference's permutes exist;
+  * the ViT residual stream is fp32 (as in the reference under autocast: cat with fp32 cls/pos promotes,
+    SURVEY.md App. D); the motion-module residual stream is fp32 too;
+  * GEMM weights are `[N, K]` row-major h16 (nn.Linear layout); 3x3 conv weights are `[Co, 9*Ci]` with
+    K = (ky*3+kx)*Ci + ci; ConvTranspose weights are `[(ky*S+kx)*Co + co, ci]`; GEGLU weights are interleaved
+    in blocks of 2*half rows `[a(half) | gate(half)]`;
+  * channel counts consumed by the implicit-GEMM conv are zero-padded to a multiple of 64 at pack time
+    (only ViT-S needs it: 48->64, 96->128, 32->64).
+
+Reference call sites are cited next to each stage.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List
+
+import torch
+
+from . import ops
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, EPI_CONVT, EPI_GEGLU, EPI_LINEAR, EPI_TAIL
+from .synth import ENCODER_DIMS
+
+KPAD_PATCH = 592   # 3*14*14 = 588 padded to a 16-byte row pitch; the GEMM's TMA zero-fills the K tail
+
+
+def _pad_to(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing helpers (pure tensor reshuffles; run once per load_state_dict)
+# ------------------------------------------------------------------------------------------------
+def pack_conv3x3(w: torch.Tensor, ci_pad: int, co_pad: int) -> torch.Tensor:
+    """[Co,Ci,3,3] -> [co_pad, 9*ci_pad], K index = (ky*3+kx)*ci_pad + ci (matches the conv-mode TMA walk)."""
+    co, ci = w.shape[:2]
+    out = torch.zeros(co_pad, 3, 3, ci_pad, dtype=w.dtype, device=w.device)
+    out[:co, :, :, :ci] = w.permute(0, 2, 3, 1)
+    return out.reshape(co_pad, 9 * ci_pad).contiguous()
+
+
+def pack_convt(w: torch.Tensor, b: torch.Tensor, co_pad: int):
+    """ConvTranspose2d weight [Ci,Co,S,S] (kernel == stride) -> [(ky*S+kx)*co_pad + co, Ci]; bias -> [co_pad]."""
+    ci, co, s, _ = w.shape
+    out = torch.zeros(s, s, co_pad, ci, dtype=w.dtype, device=w.device)
+    out[:, :, :co, :] = w.permute(2, 3, 1, 0)
+    bp = torch.zeros(co_pad, dtype=torch.float32, device=w.device)
+    bp[:co] = b.float()
+    return out.reshape(s * s * co_pad, ci).contiguous(), bp
+
+
+def pack_geglu(w: torch.Tensor, b: torch.Tensor, half: int):
+    """GEGLU proj weight [2*inner, C] (rows: value | gate, motion_module/attention.py:382-384) -> row blocks
+    [value(half) | gate(half)] so one GEMM tile holds both operands of a*gelu(g)."""
+    inner = w.shape[0] // 2
+    assert inner % half == 0
+    a, g = w[:inner].reshape(inner // half, half, -1), w[inner:].reshape(inner // half, half, -1)
+    wp = torch.cat([a, g], dim=1).reshape(2 * inner, -1).contiguous()
+    ba, bg = b[:inner].reshape(inner // half, half), b[inner:].reshape(inner // half, half)
+    bp = torch.cat([ba, bg], dim=1).reshape(2 * inner).contiguous().float()
+    return wp, bp
+
+
+class Engine:
+    def __init__(self, encoder: str, features: int, out_channels: List[int], dtype=torch.bfloat16,
+                 device="cuda", num_frames: int = 32):
+        if encoder not in ENCODER_DIMS:
+            raise ValueError(f"unknown encoder {encoder!r}")
+        self.encoder = encoder
+        e = ENCODER_DIMS[encoder]
+        self.D, self.depth, self.heads, self.taps = e["embed_dim"], e["depth"], e["num_heads"], e["taps"]
+        self.F = features
+        self.oc = list(out_channels)
+        self.dtype = dtype
+        self.device = torch.device(device)
+        self.num_frames = num_frames
+        self.w: Dict[str, torch.Tensor] = {}
+        self._pos_cache: Dict[tuple, torch.Tensor] = {}
+        self.loaded = False
+        # channel paddings (see module docstring)
+        self.c_l1 = _pad_to(self.oc[0], 64)
+        self.c_l2 = _pad_to(self.oc[1], 64)
+        self.c_oc1 = _pad_to(self.F // 2, 64)
+        assert self.oc[2] % 64 == 0 and self.oc[3] % 64 == 0 and self.F % 64 == 0
+
+    # -------------------------------------------------------------------------------------------
+    def load(self, sd: Dict[str, torch.Tensor]) -> None:
+        dev, dt = self.device, self.dtype
+        w = self.w = {}
+        self._pos_cache = {}
+
+        def f32(k):
+            return sd[k].detach().to(dev, torch.float32).contiguous()
+
+        def h16(t):
+            return t.to(dev, torch.float32).to(dt).contiguous()
+
+        D = self.D
+        pw = sd["pretrained.patch_embed.proj.weight"].detach().to(dev, torch.float32).reshape(D, 588)
+        pwp = torch.zeros(D, KPAD_PATCH, device=dev)
+        pwp[:, :588] = pw
+        w["pe.w"], w["pe.b"] = h16(pwp), f32("pretrained.patch_embed.proj.bias")
+        w["cls"] = f32("pretrained.cls_token").reshape(D)
+        w["pos"] = f32("pretrained.pos_embed").reshape(-1, D)
+        for i in range(self.depth):
+            p = f"pretrained.blocks.{i}."
+            for n in ("norm1", "norm2"):
+                w[f"b{i}.{n}.w"], w[f"b{i}.{n}.b"] = f32(p + n + ".weight"), f32(p + n + ".bias")
+            for n, k in (("qkv", "attn.qkv"), ("proj", "attn.proj"), ("fc1", "mlp.fc1"), ("fc2", "mlp.fc2")):
+                w[f"b{i}.{n}.w"], w[f"b{i}.{n}.b"] = h16(sd[p + k + ".weight"]), f32(p + k + ".bias")
+            w[f"b{i}.ls1"], w[f"b{i}.ls2"] = f32(p + "ls1.gamma"), f32(p + "ls2.gamma")
+        w["norm.w"], w["norm.b"] = f32("pretrained.norm.weight"), f32("pretrained.norm.bias")
+
+        h = "head."
+        oc, F = self.oc, self.F
+        for i in range(4):
+            w[f"proj{i}.w"] = h16(sd[f"{h}projects.{i}.weight"].reshape(oc[i], D))
+            w[f"proj{i}.b"] = f32(f"{h}projects.{i}.bias")
+        wt, bt = pack_convt(sd[h + "resize_layers.0.weight"].to(dev, torch.float32), sd[h + "resize_layers.0.bias"].to(dev), self.c_l1)
+        w["rs0.w"], w["rs0.b"] = h16(wt), bt
+        wt, bt = pack_convt(sd[h + "resize_layers.1.weight"].to(dev, torch.float32), sd[h + "resize_layers.1.bias"].to(dev), self.c_l2)
+        w["rs1.w"], w["rs1.b"] = h16(wt), bt
+        w["rs3.w"] = h16(pack_conv3x3(sd[h + "resize_layers.3.weight"].to(dev, torch.float32), oc[3], oc[3]))
+        w["rs3.b"] = f32(h + "resize_layers.3.bias")
+        cin = [self.c_l1, self.c_l2, oc[2], oc[3]]
+        for i in range(4):
+            w[f"rn{i + 1}.w"] = h16(pack_conv3x3(sd[f"{h}scratch.layer{i + 1}_rn.weight"].to(dev, torch.float32), cin[i], F))
+        for r in (1, 2, 3, 4):
+            rp = f"{h}scratch.refinenet{r}."
+            w[f"rf{r}.out.w"] = h16(sd[rp + "out_conv.weight"].reshape(F, F))
+            w[f"rf{r}.out.b"] = f32(rp + "out_conv.bias")
+            for u in (1, 2):
+                for c in (1, 2):
+                    k = f"{rp}resConfUnit{u}.conv{c}."
+                    w[f"rf{r}.u{u}.c{c}.w"] = h16(pack_conv3x3(sd[k + "weight"].to(dev, torch.float32), F, F))
+                    w[f"rf{r}.u{u}.c{c}.b"] = f32(k + "bias")
+        w["oc1.w"] = h16(pack_conv3x3(sd[h + "scratch.output_conv1.weight"].to(dev, torch.float32), F, self.c_oc1))
+        b = torch.zeros(self.c_oc1, device=dev)
+        b[:F // 2] = sd[h + "scratch.output_conv1.bias"].to(dev, torch.float32)
+        w["oc1.b"] = b
+        w["oc2.w"] = h16(pack_conv3x3(sd[h + "scratch.output_conv2.0.weight"].to(dev, torch.float32), self.c_oc1, 32))
+        w["oc2.b"] = f32(h + "scratch.output_conv2.0.bias")
+        w["oc3.w"] = f32(h + "scratch.output_conv2.2.weight").reshape(32)
+        self.oc3_b = float(sd[h + "scratch.output_conv2.2.bias"].reshape(-1)[0])
+
+        self.mm_c = [oc[2], oc[3], F, F]
+        for m, C in enumerate(self.mm_c):
+            t = f"{h}motion_modules.{m}.temporal_transformer."
+            w[f"mm{m}.gn.w"], w[f"mm{m}.gn.b"] = f32(t + "norm.weight"), f32(t + "norm.bias")
+            w[f"mm{m}.in.w"], w[f"mm{m}.in.b"] = h16(sd[t + "proj_in.weight"]), f32(t + "proj_in.bias")
+            w[f"mm{m}.out.w"], w[f"mm{m}.out.b"] = h16(sd[t + "proj_out.weight"]), f32(t + "proj_out.bias")
+            blk = t + "transformer_blocks.0."
+            for a in (0, 1):
+                ab = f"{blk}attention_blocks.{a}."
+                w[f"mm{m}.a{a}.qkv.w"] = h16(torch.cat([sd[ab + "to_q.weight"], sd[ab + "to_k.weight"], sd[ab + "to_v.weight"]], 0))
+                w[f"mm{m}.a{a}.o.w"], w[f"mm{m}.a{a}.o.b"] = h16(sd[ab + "to_out.0.weight"]), f32(ab + "to_out.0.bias")
+                w[f"mm{m}.a{a}.pe"] = f32(ab + "pos_encoder.pe").reshape(-1, C)
+                w[f"mm{m}.a{a}.ln.w"], w[f"mm{m}.a{a}.ln.b"] = f32(f"{blk}norms.{a}.weight"), f32(f"{blk}norms.{a}.bias")
+            w[f"mm{m}.ffn.w"], w[f"mm{m}.ffn.b"] = f32(blk + "ff_norm.weight"), f32(blk + "ff_norm.bias")
+            half = 128 if (4 * C) % 128 == 0 else 64
+            wp, bp = pack_geglu(sd[blk + "ff.net.0.proj.weight"].to(dev, torch.float32),
+                                sd[blk + "ff.net.0.proj.bias"].to(dev, torch.float32), half)
+            w[f"mm{m}.ff0.w"], w[f"mm{m}.ff0.b"] = h16(wp), bp
+            self.__dict__.setdefault("mm_half", {})[m] = half
+            w[f"mm{m}.ff2.w"], w[f"mm{m}.ff2.b"] = h16(sd[blk + "ff.net.2.weight"]), f32(blk + "ff.net.2.bias")
+        self.loaded = True
+
+    # -------------------------------------------------------------------------------------------
+    def _pos(self, hp: int, wp: int) -> torch.Tensor:
+        """dinov2.py:179-210; cached per grid (the reference recomputes it every call)."""
+        key = (hp, wp)
+        if key not in self._pos_cache:
+            pos = self.w["pos"]
+            S = int(round(math.sqrt(pos.shape[0] - 1)))
+            if hp == S and wp == S:
+                self._pos_cache[key] = pos
+            else:
+                self._pos_cache[key] = ops.pos_embed_bicubic(pos, hp, wp)
+        return self._pos_cache[key]
+
+    def _new(self, *shape, dtype=None):
+        return torch.empty(*shape, dtype=dtype or self.dtype, device=self.device)
+
+    # -------------------------------------------------------------------------------------------
+    def encode(self, x: torch.Tensor, stages=None) -> List[torch.Tensor]:
+        """DINOv2 get_intermediate_layers (dinov2.py:297-321).  x fp32 [BT,3,H,W] -> 4 x h16 [BT*P, D]."""
+        w, D = self.w, self.D
+        BT, _, H, W = x.shape
+        hp, wp = H // 14, W // 14
+        P, N = hp * wp, hp * wp + 1
+        M = BT * N
+        pos = self._pos(hp, wp)
+        a = self._new(BT * P, KPAD_PATCH)
+        ops.patch_im2col(x, a)                                                        # patch_embed.py:66,76
+        tok = self._new(BT, N, D, dtype=torch.float32)
+        tok2 = tok.view(M, D)
+        ops.gemm(a, w["pe.w"], tok2, bias=w["pe.b"], res1=pos, row_group=P)            # + pos_embed (dinov2.py:219)
+        ops.write_cls(tok, w["cls"], pos)                                              # dinov2.py:218
+        del a
+        if stages is not None:
+            stages["tokens0"] = tok.clone()
+        ln = self._new(M, D)
+        qkv = self._new(M, 3 * D)
+        att = self._new(M, D)
+        hid = self._new(M, 4 * D)
+        taps = []
+        for i in range(self.depth):                                                   # block.py:82-107
+            b = f"b{i}."
+            ops.layernorm(tok2, w[b + "norm1.w"], w[b + "norm1.b"], 1e-6, ln)
+            ops.gemm(ln, w[b + "qkv.w"], qkv, bias=w[b + "qkv.b"])                     # attention.py:51
+            ops.attention_spatial(qkv, att, BT, N, self.heads)                         # attention.py:53-59
+            ops.gemm(att, w[b + "proj.w"], tok2, bias=w[b + "proj.b"], gamma=w[b + "ls1"], res1=tok2)
+            ops.layernorm(tok2, w[b + "norm2.w"], w[b + "norm2.b"], 1e-6, ln)
+            ops.gemm(ln, w[b + "fc1.w"], hid, bias=w[b + "fc1.b"], act=ACT_GELU)       # mlp.py:36-37
+            ops.gemm(hid, w[b + "fc2.w"], tok2, bias=w[b + "fc2.b"], gamma=w[b + "ls2"], res1=tok2)
+            if stages is not None:
+                stages[f"block{i}"] = tok.clone()
+            if i in self.taps:                                                         # dinov2.py:309-312
+                t = self._new(BT * P, D)
+                ops.layernorm(tok2, w["norm.w"], w["norm.b"], 1e-6, t, drop_group=N)
+                taps.append(t)
+        return taps
+
+    # -------------------------------------------------------------------------------------------
+    def _conv3(self, x, key, n, H, W, ci, co, **kw):
+        out = kw.pop("out", None)
+        if out is None:
+            out = self._new(n * H * W, co)
+        return ops.gemm(x, self.w[key + ".w"], out, bias=self.w.get(key + ".b"), conv_shape=(n, H, W, ci), **kw)
+
+    def _rcu(self, r, u, x, x_relu, n, H, W, extra=None, want_relu=False):
+        """ResidualConvUnit (util/blocks.py:68-91): conv2(relu(conv1(relu(x)))) + x [+ extra]."""
+        F = self.F
+        t = self._conv3(x_relu, f"rf{r}.u{u}.c1", n, H, W, F, F, act=ACT_RELU)
+        out = self._new(n * H * W, F)
+        out_relu = self._new(n * H * W, F) if want_relu else None
+        self._conv3(t, f"rf{r}.u{u}.c2", n, H, W, F, F, out=out, res1=x, res2=extra, out_relu=out_relu)
+        return out, out_relu
+
+    def _fusion(self, r, x0, skip, skip_relu, n, H, W, oh, ow):
+        """FeatureFusionBlock (util/blocks.py:135-162).  x0: upstream path (None for refinenet4),
+        skip / skip_relu: layer_rn output and its relu'd copy.  The 1x1 out_conv is applied BEFORE the bilinear
+        upsample: the two commute exactly in real arithmetic (interpolation weights sum to one) and it is 4x
+        cheaper there."""
+        F = self.F
+        if x0 is None:
+            cur, cur_relu = skip, skip_relu
+        else:
+            cur, cur_relu = self._rcu(r, 1, skip, skip_relu, n, H, W, extra=x0, want_relu=True)
+        u, _ = self._rcu(r, 2, cur, cur_relu, n, H, W)
+        o = self._new(n * H * W, F)
+        ops.gemm(u, self.w[f"rf{r}.out.w"], o, bias=self.w[f"rf{r}.out.b"])
+        up = self._new(n * oh * ow, F)
+        ops.bilinear_nhwc(o, up, n, H, W, oh, ow, F)
+        return up
+
+    def _motion(self, m, x, B, T, hw):
+        """TemporalModule (motion_module.py:60-65, 102-126, 164-177).  x h16 [B*T*hw, C] rows (b, f, pos)."""
+        w, C = self.w, self.mm_c[m]
+        M = B * T * hw
+        p = f"mm{m}."
+        gn = self._new(M, C)
+        ops.groupnorm(x, w[p + "gn.w"], w[p + "gn.b"], 1e-6, gn, B * T, hw)              # :110
+        h = self._new(M, C, dtype=torch.float32)
+        ops.gemm(gn, w[p + "in.w"], h, bias=w[p + "in.b"])                              # :113
+        n = gn                                                                          # reuse as LN output
+        qkv = self._new(M, 3 * C)
+        o = self._new(M, C)
+        for a in (0, 1):                                                                # :165-172
+            ops.layernorm(h, w[f"{p}a{a}.ln.w"], w[f"{p}a{a}.ln.b"], 1e-5, n, pe=w[f"{p}a{a}.pe"], pe_rows_per_frame=hw)
+            ops.gemm(n, w[f"{p}a{a}.qkv.w"], qkv)
+            for b in range(B):
+                s = slice(b * T * hw, (b + 1) * T * hw)
+                ops.attention_temporal(qkv[s], o[s], T, hw, C)
+            ops.gemm(o, w[f"{p}a{a}.o.w"], h, bias=w[f"{p}a{a}.o.b"], res1=h)
+        ops.layernorm(h, w[p + "ffn.w"], w[p + "ffn.b"], 1e-5, n)                        # :174
+        g = self._new(M, 4 * C)
+        ops.gemm(n, w[p + "ff0.w"], g, bias=w[p + "ff0.b"], epilogue=EPI_GEGLU, geglu_half=self.mm_half[m])
+        h16 = o
+        ops.gemm(g, w[p + "ff2.w"], h16, bias=w[p + "ff2.b"], res1=h)                    # ff + residual, h16 out
+        out = self._new(M, C)
+        ops.gemm(h16, w[p + "out.w"], out, bias=w[p + "out.b"], res1=x)                  # :120-125
+        return out
+
+    def head(self, taps, B, T, hp, wp, stages=None) -> torch.Tensor:
+        """DPTHeadTemporal.forward (dpt_temporal.py:53-114) -> fp32 [B*T, 14hp, 14wp]."""
+        w, F, oc = self.w, self.F, self.oc
+        BT = B * T
+        P = hp * wp
+        pr = []
+        for i in range(4):                                                              # :66 projects[i]
+            o = self._new(BT * P, oc[i])
+            ops.gemm(taps[i], w[f"proj{i}.w"], o, bias=w[f"proj{i}.b"])
+            pr.append(o)
+        h1, w1, h2, w2 = 4 * hp, 4 * wp, 2 * hp, 2 * wp
+        h4, w4 = (hp - 1) // 2 + 1, (wp - 1) // 2 + 1
+        l1 = self._new(BT * h1 * w1, self.c_l1)                                          # :67 resize_layers
+        ops.gemm(pr[0], w["rs0.w"], l1, bias=w["rs0.b"], epilogue=EPI_CONVT, convt=(4, self.c_l1, hp, wp))
+        l2 = self._new(BT * h2 * w2, self.c_l2)
+        ops.gemm(pr[1], w["rs1.w"], l2, bias=w["rs1.b"], epilogue=EPI_CONVT, convt=(2, self.c_l2, hp, wp))
+        l3 = pr[2]
+        col = ops.im2col3x3_s2(pr[3], BT, hp, wp, oc[3])
+        l4 = self._new(BT * h4 * w4, oc[3])
+        ops.gemm(col, w["rs3.w"], l4, bias=w["rs3.b"])
+        del col
+        if stages is not None:
+            stages.update(layer_1=(l1, h1, w1), layer_2=(l2, h2, w2), layer_3=(l3, hp, wp), layer_4=(l4, h4, w4))
+        l3 = self._motion(0, l3, B, T, P)                                               # :75
+        l4 = self._motion(1, l4, B, T, h4 * w4)                                         # :76
+        if stages is not None:
+            stages.update(mm0=(l3, hp, wp), mm1=(l4, h4, w4))
+
+        def rn(i, x, H, W, ci):                                                         # :78-81 layer{i}_rn (+ relu'd copy)
+            o, orl = self._new(BT * H * W, F), self._new(BT * H * W, F)
+            ops.gemm(x, w[f"rn{i}.w"], o, conv_shape=(BT, H, W, ci), out_relu=orl)
+            return o, orl
+
+        l1r, l1rr = rn(1, l1, h1, w1, self.c_l1)
+        l2r, l2rr = rn(2, l2, h2, w2, self.c_l2)
+        l3r, l3rr = rn(3, l3, hp, wp, oc[2])
+        l4r, l4rr = rn(4, l4, h4, w4, oc[3])
+        del l1, l2, l4
+        if stages is not None:
+            stages.update(layer_1_rn=(l1r, h1, w1), layer_2_rn=(l2r, h2, w2), layer_3_rn=(l3r, hp, wp), layer_4_rn=(l4r, h4, w4))
+        p4 = self._fusion(4, None, l4r, l4rr, BT, h4, w4, hp, wp)                        # :83
+        if stages is not None:
+            stages["path_4_pre"] = (p4, hp, wp)
+        p4 = self._motion(2, p4, B, T, P)                                               # :84
+        p3 = self._fusion(3, p4, l3r, l3rr, BT, hp, wp, h2, w2)                          # :85
+        if stages is not None:
+            stages.update(path_4=(p4, hp, wp), path_3_pre=(p3, h2, w2))
+        p3 = self._motion(3, p3, B, T, h2 * w2)                                         # :86
+        p2 = self._fusion(2, p3, l2r, l2rr, BT, h2, w2, h1, w1)                          # :90/103
+        p1 = self._fusion(1, p2, l1r, l1rr, BT, h1, w1, 2 * h1, 2 * w1)                  # :91/104
+        if stages is not None:
+            stages.update(path_3=(p3, h2, w2), path_2=(p2, h1, w1), path_1=(p1, 2 * h1, 2 * w1))
+        del l1r, l1rr, l2r, l2rr, l3r, l3rr, l4r, l4rr, p2, p3, p4
+        H8, W8 = 2 * h1, 2 * w1
+        o1 = self._conv3(p1, "oc1", BT, H8, W8, F, self.c_oc1)                           # :92/105 output_conv1
+        if stages is not None:
+            stages["output_conv1"] = (o1, H8, W8)
+        del p1
+        H, W = 14 * hp, 14 * wp
+        depth = self._new(BT, H, W, dtype=torch.float32)
+        up = self._new(H * W, self.c_oc1)
+        o1v = o1.view(BT, H8 * W8, self.c_oc1)
+        for f in range(BT):   # per frame: the upsampled 128-channel map (69 MB at 518^2) stays L2-resident
+            ops.bilinear_nhwc(o1v[f], up, 1, H8, W8, H, W, self.c_oc1)                   # :94-96
+            ops.gemm(up, w["oc2.w"], depth[f], bias=w["oc2.b"], epilogue=EPI_TAIL, tail_w=w["oc3.w"],
+                     tail_b=self.oc3_b, conv_shape=(1, H, W, self.c_oc1))                # :97-100 output_conv2
+        return depth
+
+    # -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, stages=None) -> torch.Tensor:
+        """VideoDepthAnything.forward (video_depth.py:89-164): x [B,T,3,H,W] -> fp32 [B,T,H,W]."""
+        if not self.loaded:
+            raise RuntimeError("weights not loaded (call load_state_dict first)")
+        if x.dim() != 5 or x.shape[2] != 3:
+            raise ValueError(f"expected x of shape [B,T,3,H,W], got {tuple(x.shape)}")
+        B, T, _, H, W = x.shape
+        assert H % 14 == 0, f"Input image height {H} is not a multiple of patch height 14"    # patch_embed.py:73
+        assert W % 14 == 0, f"Input image width {W} is not a multiple of patch width: 14"     # patch_embed.py:74
+        if T > self.num_frames:
+            raise ValueError(f"T={T} exceeds temporal_max_len={self.num_frames} (dpt_temporal.py:38)")
+        if not x.is_cuda:
+            raise RuntimeError("the engine has no CPU path; move the input to the B200")
+        x = x.to(torch.float32).contiguous().flatten(0, 1)
+        hp, wp = H // 14, W // 14
+        taps = self.encode(x, stages)
+        if stages is not None:
+            for i, t in enumerate(taps):
+                stages[f"tap{i}"] = t
+        depth = self.head(taps, B, T, hp, wp, stages)
+        # video_depth.py:162-163: bilinear to (H,W) is the identity (14*hp == H) and the ReLU is already applied
+        return depth.view(B, T, H, W)

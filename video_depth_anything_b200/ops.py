@@ -1,0 +1,208 @@
+"""Thin torch-tensor wrappers over the libvda C ABI.  torch is only used for device memory and streams; every
+arithmetic operation below runs in the hand-written sm_100a kernels.  Each wrapper names the reference operator
+it replaces."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (A_CONV3, A_PLAIN, ACT_GELU, ACT_NONE, ACT_RELU, EPI_CONVT, EPI_GEGLU, EPI_LINEAR, EPI_TAIL,
+                   GemmParams, VDA_BF16, VDA_FP16, check)
+
+LAUNCHES = 0   # number of libvda kernels-launching calls issued (bench.py reports it as gpu_launches)
+
+
+def dt_code(t: torch.dtype) -> int:
+    if t == torch.bfloat16:
+        return VDA_BF16
+    if t == torch.float16:
+        return VDA_FP16
+    raise TypeError(f"16-bit operand type must be bfloat16 or float16, got {t}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda, "libvda operates on CUDA tensors only (no CPU fallback)"
+    return t.data_ptr()
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def gemm(a: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, bias=None, gamma=None, act=ACT_NONE,
+         res1=None, res2=None, out_relu=None, row_group=0, epilogue=EPI_LINEAR,
+         conv_shape=None, geglu_half=0, convt=None, tail_w=None, tail_b=0.0, M=None) -> torch.Tensor:
+    """out = epilogue(a @ wt.T).  a: [M,K] h16 (row stride allowed) or NHWC [n,H,W,C] with conv_shape=(n,H,W,C);
+    wt: [N,K] h16 contiguous.  Replaces F.linear / F.conv2d(1x1, 3x3 s1 p1) / F.conv_transpose2d(k == s)."""
+    lib = _lib.load()
+    p = GemmParams()
+    N, K = wt.shape
+    assert wt.is_contiguous() and wt.dtype == a.dtype
+    p.N, p.K, p.dtype = N, K, dt_code(a.dtype)
+    p.epilogue = epilogue
+    if conv_shape is not None:
+        n, H, W, Cc = conv_shape
+        assert a.is_contiguous() and a.numel() == n * H * W * Cc
+        p.a_mode, p.n_img, p.H, p.W, p.C = A_CONV3, n, H, W, Cc
+        p.M, p.lda = n * H * W, Cc
+    else:
+        assert a.dim() == 2 and a.stride(1) == 1
+        p.a_mode = A_PLAIN
+        p.M, p.lda = (a.shape[0] if M is None else M), a.stride(0)
+        assert a.shape[1] == K, (a.shape, wt.shape)
+    p.A, p.Wt = _p(a), _p(wt)
+    p.bias, p.gamma, p.act = _p(bias), _p(gamma), act
+    if res1 is not None:
+        p.res1, p.ldr1, p.res1_f32 = _p(res1), res1.stride(-2), int(res1.dtype == torch.float32)
+        assert res1.stride(-1) == 1 and (res1.dtype == torch.float32 or res1.dtype == a.dtype)
+    if res2 is not None:
+        assert res2.dtype == a.dtype and res2.stride(-1) == 1
+        p.res2 = _p(res2)
+    p.out, p.out_f32 = _p(out), int(out.dtype == torch.float32)
+    assert out.dtype == torch.float32 or out.dtype == a.dtype
+    if epilogue == EPI_TAIL:
+        p.ldo = 1
+        p.tail_w, p.tail_b = _p(tail_w), float(tail_b)
+    else:
+        assert out.stride(-1) == 1
+        p.ldo = out.stride(-2)
+        if res2 is not None:
+            assert res2.stride(-2) == p.ldo
+        if out_relu is not None:
+            assert out_relu.stride(-2) == p.ldo and out_relu.dtype == a.dtype
+    p.out_relu = _p(out_relu)
+    p.row_group = row_group
+    p.geglu_half = geglu_half
+    if convt is not None:
+        p.convt_s, p.convt_co, p.in_h, p.in_w = convt
+    check(lib.vda_gemm(C.byref(p), _stream()))
+    _count()
+    return out
+
+
+def layernorm(x: torch.Tensor, w, b, eps: float, out: torch.Tensor, *, drop_group=0, pe=None, pe_rows_per_frame=0):
+    """nn.LayerNorm over the last dim; x fp32 or h16 [rows, C] -> out h16."""
+    lib = _lib.load()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    assert x.is_contiguous() and out.is_contiguous()
+    check(lib.vda_layernorm(_p(x), int(x.dtype == torch.float32), _p(out), _p(w), _p(b), eps, rows, Cc,
+                            dt_code(out.dtype), drop_group, _p(pe), pe_rows_per_frame,
+                            0 if pe is None else pe.shape[0], _stream()))
+    _count()
+    return out
+
+
+def groupnorm(x: torch.Tensor, w, b, eps: float, out: torch.Tensor, frames: int, hw: int, groups: int = 32):
+    """nn.GroupNorm(groups, C) per frame over NHWC h16 [frames, hw, C]."""
+    lib = _lib.load()
+    Cc = x.shape[-1]
+    stats = torch.empty(frames * groups * 2, dtype=torch.float32, device=x.device)
+    check(lib.vda_groupnorm(_p(x), _p(out), _p(w), _p(b), eps, frames, hw, Cc, groups, _p(stats), dt_code(x.dtype),
+                            _stream()))
+    _count(2)
+    return out
+
+
+def attention_spatial(qkv: torch.Tensor, out: torch.Tensor, frames: int, N: int, heads: int):
+    lib = _lib.load()
+    assert qkv.is_contiguous() and out.is_contiguous()
+    check(lib.vda_attention_spatial(_p(qkv), _p(out), frames, N, heads, dt_code(qkv.dtype), _stream()))
+    _count()
+    return out
+
+
+def attention_temporal(qkv: torch.Tensor, out: torch.Tensor, T: int, hw: int, Cc: int, heads: int = 8):
+    lib = _lib.load()
+    assert qkv.is_contiguous() and out.is_contiguous()
+    check(lib.vda_attention_temporal(_p(qkv), _p(out), T, hw, Cc, heads, dt_code(qkv.dtype), _stream()))
+    _count()
+    return out
+
+
+def patch_im2col(x: torch.Tensor, out: torch.Tensor):
+    """x fp32 [frames,3,H,W] -> out h16 [frames*hp*wp, kpad]"""
+    lib = _lib.load()
+    frames, _, H, W = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float32
+    check(lib.vda_patch_im2col(_p(x), _p(out), frames, H, W, out.shape[1], dt_code(out.dtype), _stream()))
+    _count()
+    return out
+
+
+def write_cls(tokens: torch.Tensor, cls_token: torch.Tensor, pos: torch.Tensor):
+    lib = _lib.load()
+    frames, tpf, D = tokens.shape
+    check(lib.vda_write_cls(_p(tokens), _p(cls_token), _p(pos), frames, tpf, D, _stream()))
+    _count()
+
+
+def pos_embed_bicubic(pos_in: torch.Tensor, hp: int, wp: int) -> torch.Tensor:
+    lib = _lib.load()
+    n, D = pos_in.shape
+    S = int(round((n - 1) ** 0.5))
+    out = torch.empty(1 + hp * wp, D, dtype=torch.float32, device=pos_in.device)
+    check(lib.vda_pos_embed_bicubic(_p(pos_in), _p(out), S, hp, wp, D, _stream()))
+    _count()
+    return out
+
+
+def im2col3x3_s2(x: torch.Tensor, n: int, H: int, W: int, Cc: int) -> torch.Tensor:
+    lib = _lib.load()
+    oh, ow = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(n * oh * ow, 9 * Cc, dtype=x.dtype, device=x.device)
+    check(lib.vda_im2col3x3_s2(_p(x), _p(out), n, H, W, Cc, dt_code(x.dtype), _stream()))
+    _count()
+    return out
+
+
+def bilinear_nhwc(x: torch.Tensor, out: torch.Tensor, n: int, ih: int, iw: int, oh: int, ow: int, Cc: int):
+    lib = _lib.load()
+    check(lib.vda_bilinear_nhwc(_p(x), _p(out), n, ih, iw, oh, ow, Cc, dt_code(x.dtype), _stream()))
+    _count()
+    return out
+
+
+def bilinear_f32(x: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+    lib = _lib.load()
+    n, ih, iw = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float32
+    out = torch.empty(n, oh, ow, dtype=torch.float32, device=x.device)
+    check(lib.vda_bilinear_f32(_p(x), _p(out), n, ih, iw, oh, ow, _stream()))
+    _count()
+    return out
+
+
+def add_h16(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor):
+    lib = _lib.load()
+    check(lib.vda_add_h16(_p(a), _p(b), _p(out), a.numel(), dt_code(a.dtype), _stream()))
+    _count()
+    return out
+
+
+def lsq_scale_shift(pred: torch.Tensor, target: torch.Tensor, scale_shift: torch.Tensor, scratch: torch.Tensor):
+    lib = _lib.load()
+    assert pred.is_contiguous() and target.is_contiguous() and pred.numel() == target.numel()
+    assert scratch.dtype == torch.float64 and scratch.numel() >= 5
+    check(lib.vda_lsq_scale_shift(_p(pred), _p(target), pred.numel(), _p(scale_shift), _p(scratch), _stream()))
+    _count(2)
+
+
+def affine_clamp_blend(x: torch.Tensor, scale_shift: torch.Tensor, out: torch.Tensor, prev=None, blend_w=None):
+    lib = _lib.load()
+    frames = x.shape[0]
+    hw = x.numel() // frames
+    assert x.is_contiguous() and out.is_contiguous()
+    check(lib.vda_affine_clamp_blend(_p(x), _p(scale_shift), _p(prev), _p(blend_w), _p(out), frames, hw, _stream()))
+    _count()
+    return out

@@ -1,0 +1,80 @@
+"""Host-side logic of the long-video driver: window bookkeeping, resize geometry and frame preprocessing.
+
+Reference: video_depth_anything/video_depth.py:166-201 and util/transform.py:62-158."""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import numpy as np
+
+# video_depth.py:29-33 — "infer settings, do not change"
+INFER_LEN = 32
+OVERLAP = 10
+KEYFRAMES = [0, 12, 24, 25, 26, 27, 28, 29, 30, 31]
+INTERP_LEN = 8
+STEP = INFER_LEN - OVERLAP
+
+_MEAN = np.array([0.485, 0.456, 0.406], dtype=np.float64)
+_STD = np.array([0.229, 0.224, 0.225], dtype=np.float64)
+
+
+def num_windows(n_frames: int) -> int:
+    return -(-n_frames // STEP)
+
+
+def window_source_indices(n_frames: int) -> List[List[int]]:
+    """Source frame of every slot of every window.  The reference pads the frame list with copies of the last
+    frame (video_depth.py:187-191), slices 32 frames every 22, and overwrites the first 10 slots with the
+    previous window's KEYFRAMES slots (:200-201).  Unrolled, that recurrence has the closed form
+        window 0 : 0..31
+        window k : [0, 22k-10, 22k+2, ..., 22k+31]      (indices clipped to n-1)
+    so windows depend on input frames only and can be computed in any order / on any GPU."""
+    if n_frames <= 0:
+        raise ValueError("empty video")
+    out = []
+    for k in range(num_windows(n_frames)):
+        if k == 0:
+            idx = list(range(INFER_LEN))
+        else:
+            idx = [0, STEP * k - OVERLAP] + [STEP * k + 2 + j for j in range(INFER_LEN - 2)]
+        out.append([min(i, n_frames - 1) for i in idx])
+    return out
+
+
+def _constrain(x: float, min_val: int) -> int:
+    y = int(np.round(x / 14) * 14)
+    if y < min_val:
+        y = int(np.ceil(x / 14) * 14)
+    return y
+
+
+def get_resize_hw(h0: int, w0: int, input_size: int = 518):
+    """Network input size for an (h0, w0) video: aspect guard (video_depth.py:167-171) then Resize.get_size with
+    keep_aspect_ratio / lower_bound / multiple of 14 (util/transform.py:62-107)."""
+    ratio = max(h0, w0) / min(h0, w0)
+    if ratio > 1.78:
+        input_size = int(input_size * 1.777 / ratio)
+        input_size = round(input_size / 14) * 14
+    scale_h, scale_w = input_size / h0, input_size / w0
+    if scale_w > scale_h:
+        scale_h = scale_w
+    else:
+        scale_w = scale_h
+    return _constrain(scale_h * h0, input_size), _constrain(scale_w * w0, input_size)
+
+
+def preprocess_frames(frames: np.ndarray, indices: Iterable[int], input_size: int = 518) -> np.ndarray:
+    """uint8 [N,H0,W0,3] RGB -> float32 [len(indices),3,nh,nw]: /255, cv2 INTER_CUBIC resize, ImageNet normalise in
+    float64, CHW (util/transform.py:109-158 as composed at video_depth.py:173-185,198).  Each source frame is
+    processed once (the reference redoes the overlap frames for every window)."""
+    import cv2
+    indices = list(indices)
+    h0, w0 = frames.shape[1:3]
+    nh, nw = get_resize_hw(h0, w0, input_size)
+    out = np.empty((len(indices), 3, nh, nw), dtype=np.float32)
+    for j, i in enumerate(indices):
+        img = frames[i].astype(np.float32) / 255.0
+        img = cv2.resize(img, (nw, nh), interpolation=cv2.INTER_CUBIC)
+        img = (img - _MEAN) / _STD
+        out[j] = np.transpose(img, (2, 0, 1))
+    return out
