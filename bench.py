@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the Video-Depth-Anything hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--encoder vitl] [--dtype bf16]
+
+A "step" is one forward pass of one 1x32x518x518 window (BASELINE.json configs[1]) per GPU.  N>1 is launched by
+torchrun (one rank per GPU, NCCL); windows are independent in model compute, so ranks process
+their own windows with no data-path collective and the aggregate is reported as weak scaling.
+
+Printed JSON (rank 0, one line):
+  value        model frames/s, inputs resident in HBM, timed with CUDA events, max over ranks
+  e2e          same metric through the public API with HOST buffers: pinned H2D of the window + forward + D2H of
+               the depth map inside the timed region
+  roofline     dominant kernel family = the tcgen05 GEMM/implicit-conv kernel; achieved = algorithmic FLOPs of
+               those launches / their CUDA-event time, measured in the timed region; peak = MEASURED_PEAKS.json
+  cpu_baseline the oracle port (oracle/vda_oracle.py, torch fp32 on the host cores) on a bounded sample
+`--impl reference` times that CPU port alone (the reference itself is Python/PyTorch on CPU; /root/reference does
+not exist on the GPU box, the oracle is its pinned restatement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_TFLOP_PER_WINDOW = {"vitl": 44.950, "vits": 3.881}     # SURVEY.md §6 / BASELINE.md §2 (32x518x518)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(burst=d["bf16_tflops"], sustained=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"], src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_ev = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=3)
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_frames_per_s(encoder: str, frames: int, steps: int = 1, warmup: int = 0):
+    """The reference's fp32 CPU path (oracle port) on a bounded sample: `frames` frames at 518x518."""
+    from oracle import vda_oracle as O
+    from video_depth_anything_b200.synth import MODEL_CONFIGS, synth_state_dict
+    torch.set_num_threads(os.cpu_count())
+    sd = synth_state_dict(**MODEL_CONFIGS[encoder], seed=0)
+    x = torch.randn(1, frames, 3, 518, 518, generator=torch.Generator().manual_seed(1234))
+    for _ in range(warmup):
+        O.forward(sd, x, encoder)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.forward(sd, x, encoder)
+        ts.append(time.perf_counter() - t0)
+    return frames / (sum(ts) / len(ts)), ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = args.cpu_frames
+    fps, ts = cpu_port_frames_per_s(args.encoder, frames, steps=args.steps, warmup=min(args.warmup, 1))
+    ms = 1e3 * sum(ts) / len(ts)
+    line = {
+        "impl": "reference", "metric": "frames/s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.encoder} 1x32x518x518 window, random-init weights", "encoder": args.encoder},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{frames} of 32 frames (T={frames}) at 518x518, {args.encoder} fp32, torch CPU oracle port"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--encoder", default="vitl", choices=["vitl", "vits"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel-family time table (JSON) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from video_depth_anything_b200 import MODEL_CONFIGS, VideoDepthAnything, ops, synth_state_dict
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+
+    model = VideoDepthAnything(**MODEL_CONFIGS[args.encoder], dtype=dt)
+    model.load_state_dict(synth_state_dict(**MODEL_CONFIGS[args.encoder], seed=0))
+    model.to(dev)
+    B, T, H, Wd = 1, 32, 518, 518
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(B, T, 3, H, Wd, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = torch.empty(B, T, H, Wd, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm ----------------
+    for _ in range(W):
+        d = model.forward(x_dev)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = ops.LAUNCHES
+    ops.PROFILE = []
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for i in range(K):
+        flush.zero_()                      # evict L2 between steps (256 MB > 126 MB L2)
+        ev[i][0].record()
+        d = model.forward(x_dev)
+        ev[i][1].record()
+    t_end.record()
+    barrier()
+    prof, ops.PROFILE = ops.PROFILE, None
+    launches = ops.LAUNCHES - launches0
+    clocks = sampler.stop() if sampler else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = t_start.elapsed_time(t_end)
+    tmax = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = tmax.item()
+    frames_total = world * K * B * T
+    value = frames_total / (total_ms * 1e-3)
+    assert (d > 0).float().mean().item() > 0.99, "degenerate output"
+
+    # per-kernel-family table from the CUDA events recorded inside the timed region
+    fam = {}
+    for name, info, s, e in prof:
+        key = info.get("kind", name)
+        f = fam.setdefault(key, {"ms": 0.0, "flops": 0.0, "launches": 0})
+        f["ms"] += s.elapsed_time(e)
+        f["flops"] += info.get("flops", 0.0)
+        f["launches"] += 1
+    pk = peaks()
+    tc = [v for k, v in fam.items() if k.startswith("gemm") or k.startswith("conv3x3")]
+    tc_ms, tc_flops, tc_n = sum(v["ms"] for v in tc), sum(v["flops"] for v in tc), sum(v["launches"] for v in tc)
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 GEMM + implicit 3x3 conv, all epilogues)",
+                "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
+                "peak_kind": f"bf16_tflops_sustained of {pk['src']} (kernel timed inside a long step)",
+                "flops_per_launch": tc_flops / max(tc_n, 1), "avg_launch_ms": tc_ms / max(tc_n, 1),
+                "launches_per_step": tc_n / K, "share_of_step": tc_ms / sum(step_ms), "traffic": None}
+    whole = ALGO_TFLOP_PER_WINDOW[args.encoder] * K * B / (sum(step_ms) * 1e-3)
+
+    # ---------------- end-to-end arm (host buffers, copies in the timed region) ----------------
+    for _ in range(2):
+        model.forward(x_host.to(dev, non_blocking=True))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for i in range(K):
+        xd = x_host.to(dev, non_blocking=True)
+        dd = model.forward(xd)
+        out_host.copy_(dd, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller consumes the depth map each step
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    tm = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    e2e = {"value": frames_total / (tm.item() * 1e-3), "unit": "frames/s",
+           "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            fps, ts = cpu_port_frames_per_s(args.encoder, args.cpu_frames)
+            cpu = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"{args.cpu_frames} of 32 frames (T={args.cpu_frames}) at 518x518, {args.encoder} fp32, "
+                             f"torch CPU oracle port, {ts[0]:.1f}s"}
+        line = {
+            "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "p50_window_latency_ms": statistics.median(step_ms),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"{args.encoder} 1x32x518x518 window per GPU per step, random-init weights",
+                       "encoder": args.encoder, "frames_per_window": T, "l2": "256 MB flush between steps",
+                       "parallelism": f"window-sharded replicas x{world}"},
+            "tflops_algorithmic": whole if world == 1 else None,
+            "frac_of_bf16_sustained": (whole / pk["sustained"]) if world == 1 else None,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+        if args.profile_out:
+            tab = sorted(((k, v["ms"] / K, v["launches"] / K, v["flops"] / K / 1e12) for k, v in fam.items()),
+                         key=lambda r: -r[1])
+            json.dump({"per_step": [dict(kernel=k, ms=ms, launches=n, tflop=tf,
+                                         tflops=(tf / (ms * 1e-3) if ms > 0 else 0)) for k, ms, n, tf in tab],
+                       "step_ms": step_ms}, open(args.profile_out, "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

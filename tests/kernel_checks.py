@@ -4,8 +4,11 @@ by `python tests/kernel_checks.py` (prints a table and keeps going; handy for a 
 from __future__ import annotations
 
 import math
+import os
 import sys
 import traceback
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 import torch.nn.functional as F

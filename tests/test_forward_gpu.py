@@ -71,3 +71,16 @@ def test_stagewise_vs_oracle_vits():
     fin, rows, d, ref = stage_report("vits", 0, (1, 8, 3, 56, 70), 1234, torch.float16)
     worst = max(r[1] for r in rows)
     assert fin[0] <= TOL and worst < 0.15, (fin, rows)
+
+
+@pytest.mark.parametrize("enc,dtype,tol", [("vitl", torch.bfloat16, TOL), ("vitl", torch.float16, TOL),
+                                           ("vits", torch.bfloat16, TOL)], ids=["vitl-bf16", "vitl-fp16", "vits-bf16"])
+def test_full_size_window_vs_oracle(enc, dtype, tol):
+    """BASELINE.json configs[0]/[1]: one 1x32x518x518 window, oracle evaluated in fp32 on the same GPU
+    (TF32 off) as the checker."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    fin, rows, d, ref = stage_report(enc, 0, (1, 32, 3, 518, 518), 1234, dtype, oracle_device="cuda")
+    assert (ref > 0).float().mean() > 0.99
+    print(f"{enc} {dtype}: rel err max {fin[0]:.3e} p99.9 {fin[1]:.3e} mean {fin[2]:.3e}")
+    assert fin[0] <= tol, fin

@@ -327,18 +327,18 @@ extern "C" int vda_attention_temporal(const void* qkv, void* out, int T, int hw,
   int hpc = heads;   // heads per CTA: largest divisor of `heads` whose fp32 q|k|v tile stays <= 50 KB
   while (hpc > 1 && (heads % hpc != 0 || static_cast<size_t>(3) * T * (hpc * dh + 1) * 4 > 50 * 1024)) --hpc;
   const size_t smem = static_cast<size_t>(3) * T * (hpc * dh + 1) * sizeof(float);
-  VDA_CHECK(smem <= 200 * 1024, "temporal attention tile does not fit shared memory (head dim %d)", dh);
+  VDA_CHECK(smem <= 100 * 1024, "temporal attention tile does not fit shared memory (head dim %d)", dh);
   dim3 grid(hw, heads / hpc);
   const int threads = 32 * hpc < 64 ? 64 : 32 * hpc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == VDA_BF16) {
     auto k = temporal_attention_kernel<__nv_bfloat16>;
-    VDA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VDA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     k<<<grid, threads, smem, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), T, hw, C,
                                    heads, hpc);
   } else {
     auto k = temporal_attention_kernel<__half>;
-    VDA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VDA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     k<<<grid, threads, smem, st>>>(static_cast<const __half*>(qkv), static_cast<__half*>(out), T, hw, C, heads, hpc);
   }
   VDA_CUDA(cudaGetLastError());

@@ -414,10 +414,10 @@ static int pick_block_n(int N, int tiles_m) {
 template <typename T, int EPI, bool CONV>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, size_t smem, cudaStream_t st) {
   auto kfn = gemm_kernel<T, EPI, CONV>;
-  static bool attr_done = false;   // per instantiation
-  if (!attr_done) {
-    VDA_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
+  static size_t attr_smem = 0;   // per instantiation: largest dynamic smem opted in so far
+  if (smem > attr_smem) {
+    VDA_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem = smem;
   }
   const int grid = d.num_tiles < sm_count() ? d.num_tiles : sm_count();
   kfn<<<grid, kThreads, smem, st>>>(tmA, tmB, d);

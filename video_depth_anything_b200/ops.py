@@ -12,7 +12,9 @@ from . import _lib
 from ._lib import (A_CONV3, A_PLAIN, ACT_GELU, ACT_NONE, ACT_RELU, EPI_CONVT, EPI_GEGLU, EPI_LINEAR, EPI_TAIL,
                    GemmParams, VDA_BF16, VDA_FP16, check)
 
-LAUNCHES = 0   # number of libvda kernels-launching calls issued (bench.py reports it as gpu_launches)
+LAUNCHES = 0   # number of libvda kernel launches issued (bench.py reports it as gpu_launches)
+PROFILE = None  # when a list: every op appends (name, info dict, start_event, end_event)   [bench.py / tools]
+_INFO = {}
 
 
 def dt_code(t: torch.dtype) -> int:
@@ -85,6 +87,9 @@ def gemm(a: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, bias=None, gam
     p.geglu_half = geglu_half
     if convt is not None:
         p.convt_s, p.convt_co, p.in_h, p.in_w = convt
+    if PROFILE is not None:
+        _INFO.update(kind=("conv3x3" if conv_shape is not None else "gemm") + f"/epi{epilogue}",
+                     M=int(p.M), N=int(N), K=int(K), flops=2.0 * p.M * N * K)
     check(lib.vda_gemm(C.byref(p), _stream()))
     _count()
     return out
@@ -117,6 +122,8 @@ def groupnorm(x: torch.Tensor, w, b, eps: float, out: torch.Tensor, frames: int,
 def attention_spatial(qkv: torch.Tensor, out: torch.Tensor, frames: int, N: int, heads: int):
     lib = _lib.load()
     assert qkv.is_contiguous() and out.is_contiguous()
+    if PROFILE is not None:
+        _INFO.update(kind="attention_spatial", flops=4.0 * frames * heads * N * N * 64)
     check(lib.vda_attention_spatial(_p(qkv), _p(out), frames, N, heads, dt_code(qkv.dtype), _stream()))
     _count()
     return out
@@ -206,3 +213,26 @@ def affine_clamp_blend(x: torch.Tensor, scale_shift: torch.Tensor, out: torch.Te
     check(lib.vda_affine_clamp_blend(_p(x), _p(scale_shift), _p(prev), _p(blend_w), _p(out), frames, hw, _stream()))
     _count()
     return out
+
+
+def _profiled(fn, name):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        if PROFILE is None:
+            return fn(*a, **k)
+        _INFO.clear()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = fn(*a, **k)
+        e.record()
+        PROFILE.append((name, dict(_INFO), s, e))
+        return r
+    return wrapper
+
+
+for _n in ("gemm", "layernorm", "groupnorm", "attention_spatial", "attention_temporal", "patch_im2col", "write_cls",
+           "pos_embed_bicubic", "im2col3x3_s2", "bilinear_nhwc", "bilinear_f32", "add_h16", "lsq_scale_shift",
+           "affine_clamp_blend"):
+    globals()[_n] = _profiled(globals()[_n], _n)
