@@ -129,6 +129,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (profiling runs only)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-family time table (JSON) here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -197,9 +198,14 @@ def main():
     assert (d > 0).float().mean().item() > 0.99, "degenerate output"
 
     # per-kernel-family table from the CUDA events recorded inside the timed region
-    fam = {}
+    fam, shapes = {}, {}
     for name, info, s, e in prof:
         key = info.get("kind", name)
+        if "M" in info:
+            sh = shapes.setdefault((key, info["M"], info["N"], info["K"]), {"ms": 0.0, "flops": 0.0, "launches": 0})
+            sh["ms"] += s.elapsed_time(e)
+            sh["flops"] += info["flops"]
+            sh["launches"] += 1
         f = fam.setdefault(key, {"ms": 0.0, "flops": 0.0, "launches": 0})
         f["ms"] += s.elapsed_time(e)
         f["flops"] += info.get("flops", 0.0)
@@ -216,13 +222,13 @@ def main():
     whole = ALGO_TFLOP_PER_WINDOW[args.encoder] * K * B / (sum(step_ms) * 1e-3)
 
     # ---------------- end-to-end arm (host buffers, copies in the timed region) ----------------
-    for _ in range(2):
+    for _ in range(0 if args.no_e2e else 2):
         model.forward(x_host.to(dev, non_blocking=True))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t0 = time.perf_counter()
-    for i in range(K):
+    for i in range(0 if args.no_e2e else K):
         xd = x_host.to(dev, non_blocking=True)
         dd = model.forward(xd)
         out_host.copy_(dd, non_blocking=True)
@@ -233,8 +239,9 @@ def main():
     tm = torch.tensor([e2e_ms], device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    e2e = {"value": frames_total / (tm.item() * 1e-3), "unit": "frames/s",
-           "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4}
+    e2e = None if args.no_e2e else {"value": frames_total / (tm.item() * 1e-3), "unit": "frames/s",
+                                    "h2d_bytes_per_step": x_host.numel() * 4,
+                                    "d2h_bytes_per_step": out_host.numel() * 4}
 
     if rank == 0:
         cpu = None
@@ -260,6 +267,10 @@ def main():
                          key=lambda r: -r[1])
             json.dump({"per_step": [dict(kernel=k, ms=ms, launches=n, tflop=tf,
                                          tflops=(tf / (ms * 1e-3) if ms > 0 else 0)) for k, ms, n, tf in tab],
+                       "gemm_shapes": [dict(kernel=k[0], M=k[1], N=k[2], K=k[3], ms_per_launch=v["ms"] / v["launches"],
+                                            launches=v["launches"] / K,
+                                            tflops=v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0)
+                                       for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])],
                        "step_ms": step_ms}, open(args.profile_out, "w"), indent=1)
     if world > 1:
         dist.destroy_process_group()

@@ -47,8 +47,11 @@ def stage_report(enc, seed, shape, xseed, dtype, oracle_device="cpu"):
             v = v.permute(0, 2, 3, 1).reshape(v.shape[0], h * w, c)
         else:
             e = e.float().cpu().reshape(v.shape)
-        mx, p999, mean = O.rel_err(e, v)
-        rows.append((k, mx, mean))
+        # intermediate activations cross zero, so use a range-normalised error (per-element relative error is
+        # only meaningful for the strictly positive depth map)
+        scale = v.abs().max().item() + 1e-12
+        diff = (e - v).abs()
+        rows.append((k, diff.max().item() / scale, diff.mean().item() / scale))
     return O.rel_err(d, ref), rows, d, ref
 
 
@@ -70,7 +73,7 @@ def main():
         print(f"=== {enc} {shape} {dt}: final rel max {fin[0]:.3e} p99.9 {fin[1]:.3e} mean {fin[2]:.3e}; "
               f"depth mean {ref.mean():.4f} engine mean {d.mean():.4f}", flush=True)
         for k, mx, mean in rows:
-            print(f"    {k:14s} rel max {mx:.3e} mean {mean:.3e}", flush=True)
+            print(f"    {k:14s} range-normalised err max {mx:.3e} mean {mean:.3e}", flush=True)
 
 
 if __name__ == "__main__":

@@ -63,8 +63,25 @@ template <> struct H16<__half> {
   }
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {  // nn.GELU() default (exact erf)
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+// erf by Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below one 16-bit output ulp): branch-free,
+// ~10 FMA-pipe instructions + 2 MUFU, versus ~35 for erff -- the GELU epilogue of the fc1 GEMM is ALU-bound.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = 1.061405429f;
+  p = fmaf(p, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = __expf(-ax * ax);
+  return copysignf(fmaf(-p, e, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_erf(float x) {  // nn.GELU() default (erf form)
+  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -179,6 +196,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for outstanding tcgen05.ld; the registers are passed as in/out operands so the compiler cannot move a use
+// of the (asynchronously written) destination registers above the wait
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // misc

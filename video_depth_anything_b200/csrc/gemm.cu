@@ -22,7 +22,8 @@ namespace vda {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quadrant, each takes half of the columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 2;
 
@@ -81,44 +82,75 @@ __device__ __forceinline__ void store8f(float* dst, const float* v) {
   *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
-// ---- LINEAR epilogue on 8 consecutive columns starting at global column `col` --------------------
+// ---- LINEAR epilogue on 16 consecutive columns starting at global column `col` ------------------
+// All global loads are issued before any arithmetic / store (out may alias res1, so the compiler cannot hoist
+// loads over stores by itself): one round trip of memory latency per 16 columns instead of one per load.
 template <typename T>
-__device__ __forceinline__ void epi_linear8(const GemmDev& p, const RowInfo& ri, int col, float* v) {
-  float t[8];
-  if (p.bias) {
+__device__ __forceinline__ void epi_linear16(const GemmDev& p, const RowInfo& ri, int col, int ncols, float* v) {
+  float r1[16], r2[16];
+  const bool two = ncols > 8;
+  if (p.res1) {
+    if (p.res1_f32) {
+      const float* r = reinterpret_cast<const float*>(p.res1) + ri.res1_row * p.ldr1 + col;
+      load8f(r, r1); if (two) load8f(r + 8, r1 + 8);
+    } else {
+      const T* r = reinterpret_cast<const T*>(p.res1) + ri.res1_row * p.ldr1 + col;
+      load8<T>(r, r1); if (two) load8<T>(r + 8, r1 + 8);
+    }
+  }
+  if (p.res2) {
+    const T* r = reinterpret_cast<const T*>(p.res2) + ri.out_row * p.ldo + col;
+    load8<T>(r, r2); if (two) load8<T>(r + 8, r2 + 8);
+  }
+  if (p.bias) {   // bias / gamma are tiny, L1-resident vectors: short latency, loaded where they are used
+    float t[8];
     load8f(p.bias + col, t);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += t[i];
+    if (two) {
+      load8f(p.bias + col + 8, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 + i] += t[i];
+    }
   }
   if (p.gamma) {
+    float t[8];
     load8f(p.gamma + col, t);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] *= t[i];
+    if (two) {
+      load8f(p.gamma + col + 8, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 + i] *= t[i];
+    }
   }
   if (p.act == VDA_ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
   } else if (p.act == VDA_ACT_RELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
   }
   if (p.res1) {
-    if (p.res1_f32) load8f(reinterpret_cast<const float*>(p.res1) + ri.res1_row * p.ldr1 + col, t);
-    else load8<T>(reinterpret_cast<const T*>(p.res1) + ri.res1_row * p.ldr1 + col, t);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += t[i];
+    for (int i = 0; i < 16; ++i) v[i] += r1[i];
   }
   if (p.res2) {
-    load8<T>(reinterpret_cast<const T*>(p.res2) + ri.out_row * p.ldo + col, t);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += t[i];
+    for (int i = 0; i < 16; ++i) v[i] += r2[i];
   }
-  if (p.out_f32) store8f(reinterpret_cast<float*>(p.out) + ri.out_row * p.ldo + col, v);
-  else store8<T>(reinterpret_cast<T*>(p.out) + ri.out_row * p.ldo + col, v);
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + ri.out_row * p.ldo + col;
+    store8f(o, v); if (two) store8f(o + 8, v + 8);
+  } else {
+    T* o = reinterpret_cast<T*>(p.out) + ri.out_row * p.ldo + col;
+    store8<T>(o, v); if (two) store8<T>(o + 8, v + 8);
+  }
   if (p.out_relu) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = fmaxf(v[i], 0.f);
-    store8<T>(reinterpret_cast<T*>(p.out_relu) + ri.out_row * p.ldo + col, t);
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    T* o = reinterpret_cast<T*>(p.out_relu) + ri.out_row * p.ldo + col;
+    store8<T>(o, v); if (two) store8<T>(o + 8, v + 8);
   }
 }
 
@@ -147,7 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 128);
+      mbar_init(&tempty_bar[s], 32 * kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -225,6 +257,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else {
     // ================================ epilogue ====================================
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int eh = (warp - 2) >> 2;         // which half of the tile's columns this warp drains
     const int r = q * 32 + lane;            // row of the tile owned by this thread
     int as = 0;
     uint32_t aphase = 0;
@@ -260,53 +293,89 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                            (p.in_w * p.convt_s) + static_cast<long long>(x) * p.convt_s;
         }
       }
+      const int col_base = n_blk * p.block_n;
+      if (EPI == VDA_EPI_LINEAR && ri.valid && (p.res1 || p.res2)) {
+        // pull this thread's residual segment towards L2 while the tile's MMAs are still running
+        const int nch = p.block_n >> 4;
+        const int c_lo = col_base + (eh ? (nch + 1) / 2 : 0) * 16;
+        int c_hi = col_base + (eh ? nch : (nch + 1) / 2) * 16;
+        if (c_hi > p.N) c_hi = p.N;
+        if (p.res1) {
+          const int esz = p.res1_f32 ? 4 : 2;
+          const char* base = reinterpret_cast<const char*>(p.res1) + (ri.res1_row * p.ldr1 + c_lo) * esz;
+          for (int off = 0; off < (c_hi - c_lo) * esz; off += 128) prefetch_l2(base + off);
+        }
+        if (p.res2) {
+          const char* base = reinterpret_cast<const char*>(p.res2) + (ri.out_row * p.ldo + c_lo) * 2;
+          for (int off = 0; off < (c_hi - c_lo) * 2; off += 128) prefetch_l2(base + off);
+        }
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
-      const int col_base = n_blk * p.block_n;
 
       if (EPI == VDA_EPI_LINEAR || EPI == VDA_EPI_CONVT) {
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-          uint32_t rr[16];
-          tmem_ld16(t_row + c0, rr);
-          tmem_ld_wait();
-          if (ri.valid) {
+        const int nch = p.block_n >> 4;
+        const int ch_begin = eh ? (nch + 1) / 2 : 0, ch_end = eh ? nch : (nch + 1) / 2;
+        auto process = [&](const uint32_t (&rr)[16], int c0) {
+          if (!ri.valid) return;
+          if (EPI == VDA_EPI_LINEAR) {
+            const int col = col_base + c0;
+            if (col < p.N) {
+              float v[16];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const int col = col_base + c0 + 8 * g;
-              if (col < p.N) {
-                float v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[8 * g + i]);
-                if (EPI == VDA_EPI_LINEAR) {
-                  epi_linear8<T>(p, ri, col, v);
-                } else {
-                  const int kk = col / p.convt_co;
-                  const int co = col - kk * p.convt_co;
-                  const int ky = kk / p.convt_s, kx = kk - ky * p.convt_s;
-                  float t[8];
-                  load8f(p.bias + co, t);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] += t[i];
-                  const long long orow = ri.out_row + static_cast<long long>(ky) * (p.in_w * p.convt_s) + kx;
-                  store8<T>(reinterpret_cast<T*>(p.out) + orow * p.ldo + co, v);
-                }
-              }
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
+              epi_linear16<T>(p, ri, col, p.N - col, v);
             }
+            return;
+          }
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int col = col_base + c0 + 8 * g;
+            if (col < p.N) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[8 * g + i]);
+              const int kk = col / p.convt_co;
+              const int co = col - kk * p.convt_co;
+              const int ky = kk / p.convt_s, kx = kk - ky * p.convt_s;
+              float t[8];
+              load8f(p.bias + co, t);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += t[i];
+              const long long orow = ri.out_row + static_cast<long long>(ky) * (p.in_w * p.convt_s) + kx;
+              store8<T>(reinterpret_cast<T*>(p.out) + orow * p.ldo + co, v);
+            }
+          }
+        };
+        // software-pipelined TMEM drain: the load of chunk i+1 is in flight while chunk i is processed
+        uint32_t ra[16], rb[16];
+        if (ch_begin < ch_end) tmem_ld16(t_row + ch_begin * 16, ra);
+        for (int ch = ch_begin; ch < ch_end; ch += 2) {
+          tmem_ld_wait16(ra);
+          if (ch + 1 < ch_end) tmem_ld16(t_row + (ch + 1) * 16, rb);
+          process(ra, ch * 16);
+          if (ch + 1 < ch_end) {
+            tmem_ld_wait16(rb);
+            if (ch + 2 < ch_end) tmem_ld16(t_row + (ch + 2) * 16, ra);
+            process(rb, (ch + 1) * 16);
           }
         }
       } else if (EPI == VDA_EPI_GEGLU) {
         const int half = p.geglu_half;
-        for (int c0 = 0; c0 < half; c0 += 16) {
+        const int nch = half >> 4;
+        const int ch_begin = eh ? (nch + 1) / 2 : 0, ch_end = eh ? nch : (nch + 1) / 2;
+        for (int c0 = ch_begin * 16; c0 < ch_end * 16; c0 += 16) {
           uint32_t ra[16], rg[16];
           tmem_ld16(t_row + c0, ra);
           tmem_ld16(t_row + half + c0, rg);
-          tmem_ld_wait();
+          tmem_ld_wait16(ra);
+          tmem_ld_wait16(rg);
           if (ri.valid) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const int pc = col_base + c0 + 8 * g;          // packed column of `a`
-              if (pc + half < p.N + 0 && pc < p.N) {
+              if (pc < p.N) {
                 float ba[8], bg[8], v[8];
                 load8f(p.bias + pc, ba);
                 load8f(p.bias + pc + half, bg);
@@ -323,19 +392,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else {  // VDA_EPI_TAIL: block_n == N == 32
-        float acc = p.tail_b;
-#pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          uint32_t rr[16];
-          tmem_ld16(t_row + c0, rr);
-          tmem_ld_wait();
+        if (eh == 0) {   // 32 columns only: one warp per quadrant does the whole row
+          float acc = p.tail_b;
+          uint32_t r0[16], r1[16];
+          tmem_ld16(t_row, r0);
+          tmem_ld16(t_row + 16, r1);
+          tmem_ld_wait16(r0);
+          tmem_ld_wait16(r1);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float h = fmaxf(__uint_as_float(rr[i]) + __ldg(p.bias + c0 + i), 0.f);
-            acc = fmaf(h, __ldg(p.tail_w + c0 + i), acc);
+            const float h = fmaxf(__uint_as_float(r0[i]) + __ldg(p.bias + i), 0.f);
+            acc = fmaf(h, __ldg(p.tail_w + i), acc);
           }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float h = fmaxf(__uint_as_float(r1[i]) + __ldg(p.bias + 16 + i), 0.f);
+            acc = fmaf(h, __ldg(p.tail_w + 16 + i), acc);
+          }
+          if (ri.valid) reinterpret_cast<float*>(p.out)[ri.out_row] = fmaxf(acc, 0.f);
         }
-        if (ri.valid) reinterpret_cast<float*>(p.out)[ri.out_row] = fmaxf(acc, 0.f);
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
