@@ -447,7 +447,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims,
+int make_tensor_map(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims,
                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   PFN_encodeTiled enc = get_encode();
   VDA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
@@ -462,7 +462,7 @@ static int make_map(CUtensorMap* m, int dtype, const void* base, int rank, const
 }
 
 static int g_sm_count = 0;
-static int sm_count() {
+int sm_count() {
   if (g_sm_count == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -560,14 +560,14 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
     cuuint64_t dims[4] = {(cuuint64_t)p->C, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->n_img};
     cuuint64_t strides[3] = {(cuuint64_t)p->C * 2, (cuuint64_t)p->C * 2 * p->W, (cuuint64_t)p->C * 2 * p->W * p->H};
     cuuint32_t box[4] = {64, (cuuint32_t)d.bw, (cuuint32_t)d.bh, 1};
-    if (make_map(&tmA, p->dtype, p->A, 4, dims, strides, box)) return 1;
+    if (make_tensor_map(&tmA, p->dtype, p->A, 4, dims, strides, box)) return 1;
   } else {
     VDA_CHECK(p->lda >= p->K && p->lda % 8 == 0, "lda (%lld) must be >= K and a multiple of 8", (long long)p->lda);
     d.tiles_m = (p->M + BLOCK_M - 1) / BLOCK_M;
     cuuint64_t dims[2] = {(cuuint64_t)p->K, (cuuint64_t)p->M};
     cuuint64_t strides[1] = {(cuuint64_t)p->lda * 2};
     cuuint32_t box[2] = {64, 128};
-    if (make_map(&tmA, p->dtype, p->A, 2, dims, strides, box)) return 1;
+    if (make_tensor_map(&tmA, p->dtype, p->A, 2, dims, strides, box)) return 1;
   }
 
   if (p->epilogue == VDA_EPI_GEGLU) {
@@ -595,7 +595,7 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
     cuuint64_t dims[2] = {(cuuint64_t)p->K, (cuuint64_t)p->N};
     cuuint64_t strides[1] = {(cuuint64_t)p->K * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)d.block_n};
-    if (make_map(&tmB, p->dtype, p->Wt, 2, dims, strides, box)) return 1;
+    if (make_tensor_map(&tmB, p->dtype, p->Wt, 2, dims, strides, box)) return 1;
   }
   d.stage_bytes = kABytes + static_cast<uint32_t>(d.block_n) * BLOCK_K * 2;
   // block_n*128 is a multiple of 2048 only when block_n % 16 == 0 -> every stage stays 1024-byte aligned
