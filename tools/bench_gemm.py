@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the tcgen05 GEMM / implicit-conv kernel on the shapes of the ViT-L window (CUDA events, L2
+flushed between launches, median of `iters`).  VDA_GEMM_STAGED=0|1 forces the epilogue variant (debug hook)."""
+import os
+import sys
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from video_depth_anything_b200 import ops  # noqa: E402
+from video_depth_anything_b200._lib import ACT_GELU, ACT_NONE, ACT_RELU, EPI_TAIL  # noqa: E402
+
+DT = torch.bfloat16
+flush = None
+
+
+def timeit(fn, iters=7):
+    global flush
+    if flush is None:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    return sorted(ts)[len(ts) // 2]
+
+
+def plain(name, M, N, K, **kw):
+    a = torch.randn(M, K, device="cuda").to(DT)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(DT)
+    bias = torch.randn(N, device="cuda")
+    out_f32 = kw.pop("out_f32", False)
+    res_f32 = kw.pop("res_f32", False)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.float32 if out_f32 else DT)
+    extra = {}
+    if res_f32:
+        extra = dict(res1=out, gamma=torch.ones(N, device="cuda"))
+    ms = timeit(lambda: ops.gemm(a, w, out, bias=bias, **extra, **kw))
+    print(f"{name:34s} M={M:8d} N={N:5d} K={K:5d}  {ms * 1e3:8.1f} us  {2.0 * M * N * K / ms / 1e9:7.1f} TF/s", flush=True)
+
+
+def conv(name, n, H, W, ci, co, **kw):
+    x = torch.randn(n * H * W, ci, device="cuda").to(DT)
+    w = (torch.randn(co, 9 * ci, device="cuda") / (9 * ci) ** 0.5).to(DT)
+    bias = torch.randn(co, device="cuda")
+    tail = kw.pop("tail", False)
+    if tail:
+        out = torch.zeros(n * H * W, device="cuda")
+        tw = torch.randn(32, device="cuda")
+        fn = lambda: ops.gemm(x, w, out, bias=bias, epilogue=EPI_TAIL, tail_w=tw, tail_b=0.1, conv_shape=(n, H, W, ci))
+    else:
+        out = torch.zeros(n * H * W, co, device="cuda", dtype=DT)
+        res = torch.randn(n * H * W, co, device="cuda").to(DT) if kw.pop("res", False) else None
+        fn = lambda: ops.gemm(x, w, out, bias=bias, res1=res, conv_shape=(n, H, W, ci), **kw)
+    ms = timeit(fn)
+    M = n * H * W
+    print(f"{name:34s} M={M:8d} N={co:5d} K={9 * ci:5d}  {ms * 1e3:8.1f} us  {2.0 * M * co * 9 * ci / ms / 1e9:7.1f} TF/s", flush=True)
+
+
+if __name__ == "__main__":
+    M = 43840
+    plain("qkv", M, 3072, 1024)
+    plain("proj (+ls, fp32 residual in place)", M, 1024, 1024, out_f32=True, res_f32=True)
+    plain("fc1 + GELU", M, 4096, 1024, act=ACT_GELU)
+    plain("fc2 (+ls, fp32 residual in place)", M, 1024, 4096, out_f32=True, res_f32=True)
+    plain("projects 1024->256", 43808, 256, 1024)
+    plain("out_conv 1x1 256->256 @74^2", 175232, 256, 256)
+    plain("out_conv 1x1 256->256 @148^2", 700928, 256, 256)
+    conv("RCU conv 256->256 @148^2 +res", 32, 148, 148, 256, 256, res=True)
+    conv("RCU conv 256->256 @148^2 relu", 32, 148, 148, 256, 256, act=ACT_RELU)
+    conv("RCU conv 256->256 @74^2 +res", 32, 74, 74, 256, 256, res=True)
+    conv("output_conv1 256->128 @296^2", 32, 296, 296, 256, 128)
+    conv("output_conv2 tail 128->32->1 @518^2", 1, 518, 518, 128, 32, tail=True)

@@ -80,6 +80,29 @@ __device__ __forceinline__ float erf_fast(float x) {
 __device__ __forceinline__ float gelu_erf(float x) {  // nn.GELU() default (erf form)
   return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f));
 }
+// Packed (2 x fp32 per instruction) erf-GELU: 0.5 x + 0.5 |x| erf(|x| / sqrt 2)  (x erf(x/sqrt2) is even, so no
+// sign fix-up); erf by Abramowitz & Stegun 7.1.26 with the 1/sqrt2 folded into the constants.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 d = __ffma2_rn(ax, make_float2(0.23164190f, 0.23164190f), make_float2(1.f, 1.f));   // 1 + p |x| / sqrt2
+  const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+  float2 q = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  q = __ffma2_rn(q, t, make_float2(1.421413741f, 1.421413741f));
+  q = __ffma2_rn(q, t, make_float2(-0.284496736f, -0.284496736f));
+  q = __ffma2_rn(q, t, make_float2(0.254829592f, 0.254829592f));
+  q = __fmul2_rn(q, t);
+  const float2 w = __fmul2_rn(__fmul2_rn(ax, make_float2(-0.72134752f, -0.72134752f)), ax);   // -(x^2 / 2) log2 e
+  const float2 e = make_float2(exp2f(w.x), exp2f(w.y));
+  const float2 erf_abs = __ffma2_rn(make_float2(-q.x, -q.y), e, make_float2(1.f, 1.f));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  const float2 hax = make_float2(fabsf(hx.x), fabsf(hx.y));
+  return __ffma2_rn(hax, erf_abs, hx);
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

@@ -13,6 +13,7 @@
 // descriptor, the B tensor map and loop bounds.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <mutex>
 
 #include "../../include/vda.h"
@@ -50,111 +51,81 @@ struct GemmDev {
   int convt_s, convt_co, in_h, in_w;
   const float* tail_w;
   float tail_b;
+  int staged;   // LINEAR: transpose the tile through shared memory (fp32 residual / fp32 output streams)
 };
 
-struct RowInfo {
-  bool valid;
-  long long out_row;   // row of out / res2 / out_relu (and res1 unless row_group)
-  long long res1_row;
-};
+// 4 consecutive columns as two packed fp32 pairs (FFMA2 / FADD2 / FMUL2 process a pair per instruction)
+struct F4 { float2 a, b; };
 
 template <typename T>
-__device__ __forceinline__ void store8(T* dst, const float* v) {
-  uint4 u;
-  u.x = H16<T>::pack2(v[0], v[1]);
-  u.y = H16<T>::pack2(v[2], v[3]);
-  u.z = H16<T>::pack2(v[4], v[5]);
-  u.w = H16<T>::pack2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(dst) = u;
+__device__ __forceinline__ F4 load4h(const T* src) {
+  const uint2 u = *reinterpret_cast<const uint2*>(src);
+  F4 r;
+  r.a = H16<T>::unpack2(u.x);
+  r.b = H16<T>::unpack2(u.y);
+  return r;
+}
+__device__ __forceinline__ F4 load4f(const float* src) {
+  const float4 v = *reinterpret_cast<const float4*>(src);
+  F4 r;
+  r.a = make_float2(v.x, v.y);
+  r.b = make_float2(v.z, v.w);
+  return r;
 }
 template <typename T>
-__device__ __forceinline__ void load8(const T* src, float* v) {
-  uint4 u = *reinterpret_cast<const uint4*>(src);
-  float2 a = H16<T>::unpack2(u.x), b = H16<T>::unpack2(u.y), c = H16<T>::unpack2(u.z), d = H16<T>::unpack2(u.w);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+__device__ __forceinline__ void store4h(T* dst, const F4& v) {
+  uint2 u;
+  u.x = H16<T>::pack2(v.a.x, v.a.y);
+  u.y = H16<T>::pack2(v.b.x, v.b.y);
+  *reinterpret_cast<uint2*>(dst) = u;
 }
-__device__ __forceinline__ void load8f(const float* src, float* v) {
-  float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+__device__ __forceinline__ void store4f(float* dst, const F4& v) {
+  *reinterpret_cast<float4*>(dst) = make_float4(v.a.x, v.a.y, v.b.x, v.b.y);
 }
-__device__ __forceinline__ void store8f(float* dst, const float* v) {
-  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+__device__ __forceinline__ F4 add4(const F4& x, const F4& y) {
+  F4 r;
+  r.a = __fadd2_rn(x.a, y.a);
+  r.b = __fadd2_rn(x.b, y.b);
+  return r;
 }
-
-// ---- LINEAR epilogue on 16 consecutive columns starting at global column `col` ------------------
-// All global loads are issued before any arithmetic / store (out may alias res1, so the compiler cannot hoist
-// loads over stores by itself): one round trip of memory latency per 16 columns instead of one per load.
-template <typename T>
-__device__ __forceinline__ void epi_linear16(const GemmDev& p, const RowInfo& ri, int col, int ncols, float* v) {
-  float r1[16], r2[16];
-  const bool two = ncols > 8;
-  if (p.res1) {
-    if (p.res1_f32) {
-      const float* r = reinterpret_cast<const float*>(p.res1) + ri.res1_row * p.ldr1 + col;
-      load8f(r, r1); if (two) load8f(r + 8, r1 + 8);
-    } else {
-      const T* r = reinterpret_cast<const T*>(p.res1) + ri.res1_row * p.ldr1 + col;
-      load8<T>(r, r1); if (two) load8<T>(r + 8, r1 + 8);
-    }
-  }
-  if (p.res2) {
-    const T* r = reinterpret_cast<const T*>(p.res2) + ri.out_row * p.ldo + col;
-    load8<T>(r, r2); if (two) load8<T>(r + 8, r2 + 8);
-  }
-  if (p.bias) {   // bias / gamma are tiny, L1-resident vectors: short latency, loaded where they are used
-    float t[8];
-    load8f(p.bias + col, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += t[i];
-    if (two) {
-      load8f(p.bias + col + 8, t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[8 + i] += t[i];
-    }
-  }
-  if (p.gamma) {
-    float t[8];
-    load8f(p.gamma + col, t);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= t[i];
-    if (two) {
-      load8f(p.gamma + col + 8, t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[8 + i] *= t[i];
-    }
-  }
-  if (p.act == VDA_ACT_GELU) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-  } else if (p.act == VDA_ACT_RELU) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-  }
-  if (p.res1) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += r1[i];
-  }
-  if (p.res2) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += r2[i];
-  }
-  if (p.out_f32) {
-    float* o = reinterpret_cast<float*>(p.out) + ri.out_row * p.ldo + col;
-    store8f(o, v); if (two) store8f(o + 8, v + 8);
-  } else {
-    T* o = reinterpret_cast<T*>(p.out) + ri.out_row * p.ldo + col;
-    store8<T>(o, v); if (two) store8<T>(o + 8, v + 8);
-  }
-  if (p.out_relu) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-    T* o = reinterpret_cast<T*>(p.out_relu) + ri.out_row * p.ldo + col;
-    store8<T>(o, v); if (two) store8<T>(o + 8, v + 8);
-  }
+__device__ __forceinline__ F4 mul4(const F4& x, const F4& y) {
+  F4 r;
+  r.a = __fmul2_rn(x.a, y.a);
+  r.b = __fmul2_rn(x.b, y.b);
+  return r;
+}
+__device__ __forceinline__ F4 relu4(const F4& x) {
+  F4 r;
+  r.a = make_float2(fmaxf(x.a.x, 0.f), fmaxf(x.a.y, 0.f));
+  r.b = make_float2(fmaxf(x.b.x, 0.f), fmaxf(x.b.y, 0.f));
+  return r;
+}
+__device__ __forceinline__ F4 gelu4(const F4& x) {
+  F4 r;
+  r.a = gelu_erf2(x.a);
+  r.b = gelu_erf2(x.b);
+  return r;
 }
 
-template <typename T, int EPI, bool CONV>
+// byte offset of the 16-byte slot holding columns 4*c4..4*c4+3 of `row` in a warp's 32 x 32 fp32 staging tile
+// (rows of 128 B, slots XOR-swizzled by row: conflict-free for row-per-thread writes and row-segment reads)
+__device__ __forceinline__ uint32_t stg_off(int row, int c4) {
+  return static_cast<uint32_t>(row * 128 + ((c4 ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ F4 lds128(uint32_t addr) {
+  F4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.b.x), "=f"(r.b.y) : "r"(addr)
+               : "memory");
+  return r;
+}
+
+constexpr uint32_t kStageTile = 32 * 32 * 4;            // per-warp epilogue staging tile (bytes)
+constexpr uint32_t kStagingBytes = kEpiWarps * kStageTile;
+
+template <typename T, int EPI, bool CONV, bool STAGED>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
@@ -166,7 +137,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // 1024-byte aligned operand ring (SWIZZLE_128B atoms are 8 rows x 128 B)
+  // 1024-byte aligned operand ring (SWIZZLE_128B atoms are 8 rows x 128 B), followed by the epilogue staging tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
@@ -191,225 +162,359 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n_blk = tile % p.tiles_n;
-        const int m_blk = tile / p.tiles_n;
-        int img = 0, x0 = 0, y0 = 0;
-        if (CONV) {
-          const int per_img = p.tiles_x * p.tiles_y;
-          img = m_blk / per_img;
-          const int rem = m_blk - img * per_img;
-          y0 = (rem / p.tiles_x) * p.bh;
-          x0 = (rem % p.tiles_x) * p.bw;
-        }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+    // warp-uniform control flow, one elected lane issues (see elect_one)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.tiles_n;
+      const int m_blk = tile / p.tiles_n;
+      int img = 0, x0 = 0, y0 = 0;
+      if (CONV) {
+        const int per_img = p.tiles_x * p.tiles_y;
+        img = m_blk / per_img;
+        const int rem = m_blk - img * per_img;
+        y0 = (rem / p.tiles_x) * p.bh;
+        x0 = (rem % p.tiles_x) * p.bw;
+      }
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], p.stage_bytes);
           uint8_t* sA = smem_gen + static_cast<size_t>(stage) * p.stage_bytes;
           uint8_t* sB = sA + kABytes;
           if (CONV) {
-            const int tap = kb / p.cblocks;
-            const int cb = kb - tap * p.cblocks;
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
             tma_load_4d(sA, &tmA, &full_bar[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
           } else {
             tma_load_2d(sA, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
           }
           tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * p.block_n);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (CONV && ++cb == p.cblocks) { cb = 0; ++tap; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(H16<T>::kUmmaFmt, static_cast<uint32_t>(p.block_n));
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1u);
+    const uint32_t idesc = umma_idesc(H16<T>::kUmmaFmt, static_cast<uint32_t>(p.block_n));
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * p.acc_stride;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * p.acc_stride;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sA = smem_base + stage * p.stage_bytes;
-          const uint64_t da = umma_desc_sw128(sA);
-          const uint64_t db = umma_desc_sw128(sA + kABytes);
+        const uint32_t sA = smem_base + stage * p.stage_bytes;
+        const uint64_t da = umma_desc_sw128(sA);
+        const uint64_t db = umma_desc_sw128(sA + kABytes);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // +32 bytes (16 elements) along K inside the 128-byte swizzle atom = +2 in the address field
             umma_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          if (kb == p.num_k_blocks - 1) umma_commit(&tfull_bar[as]);   // accumulator ready for the epilogue
         }
-        umma_commit(&tfull_bar[as]);       // accumulator ready for the epilogue
-        as ^= 1;
-        if (as == 0) aphase ^= 1u;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
     }
   } else {
     // ================================ epilogue ====================================
+    const int ew = warp - 2;                // 0..7
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int eh = (warp - 2) >> 2;         // which half of the tile's columns this warp drains
-    const int r = q * 32 + lane;            // row of the tile owned by this thread
+    const int eh = ew >> 2;                 // which half of the tile's columns this warp drains
+    const uint32_t stg = smem_base + p.stages * p.stage_bytes + ew * kStageTile;
+    // phase-2 mapping: 8 lanes per row (4 columns each), 4 rows per pass, 8 passes
+    const int cg = lane & 7;
+    const int rsub = lane >> 3;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.tiles_n;
       const int m_blk = tile / p.tiles_n;
-      RowInfo ri;
-      if (CONV) {
-        const int per_img = p.tiles_x * p.tiles_y;
-        const int img = m_blk / per_img;
-        const int rem = m_blk - img * per_img;
-        const int y = (rem / p.tiles_x) * p.bh + r / p.bw;
-        const int x = (rem % p.tiles_x) * p.bw + r % p.bw;
-        ri.valid = (y < p.H) && (x < p.W);
-        ri.out_row = (static_cast<long long>(img) * p.H + y) * p.W + x;
-        ri.res1_row = ri.out_row;
-      } else {
-        const long long m = static_cast<long long>(m_blk) * BLOCK_M + r;
-        ri.valid = m < p.M;
-        ri.out_row = m;
-        ri.res1_row = m;
-        if (p.row_group > 0) {
-          ri.out_row = m + m / p.row_group + 1;
-          ri.res1_row = m % p.row_group + 1;
-        }
-        if (EPI == VDA_EPI_CONVT) {
-          const int per_img = p.in_h * p.in_w;
-          const int img = static_cast<int>(m / per_img);
-          const int rem = static_cast<int>(m - static_cast<long long>(img) * per_img);
-          const int y = rem / p.in_w, x = rem - y * p.in_w;
-          // row index of output pixel (img, y*S, x*S) in the upsampled map
-          ri.out_row = (static_cast<long long>(img) * p.in_h * p.convt_s + static_cast<long long>(y) * p.convt_s) *
-                           (p.in_w * p.convt_s) + static_cast<long long>(x) * p.convt_s;
-        }
-      }
       const int col_base = n_blk * p.block_n;
-      if (EPI == VDA_EPI_LINEAR && ri.valid && (p.res1 || p.res2)) {
-        // pull this thread's residual segment towards L2 while the tile's MMAs are still running
-        const int nch = p.block_n >> 4;
-        const int c_lo = col_base + (eh ? (nch + 1) / 2 : 0) * 16;
-        int c_hi = col_base + (eh ? nch : (nch + 1) / 2) * 16;
-        if (c_hi > p.N) c_hi = p.N;
-        if (p.res1) {
-          const int esz = p.res1_f32 ? 4 : 2;
-          const char* base = reinterpret_cast<const char*>(p.res1) + (ri.res1_row * p.ldr1 + c_lo) * esz;
-          for (int off = 0; off < (c_hi - c_lo) * esz; off += 128) prefetch_l2(base + off);
-        }
-        if (p.res2) {
-          const char* base = reinterpret_cast<const char*>(p.res2) + (ri.out_row * p.ldo + c_lo) * 2;
-          for (int off = 0; off < (c_hi - c_lo) * 2; off += 128) prefetch_l2(base + off);
-        }
-      }
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
 
-      if (EPI == VDA_EPI_LINEAR || EPI == VDA_EPI_CONVT) {
-        const int nch = p.block_n >> 4;
-        const int ch_begin = eh ? (nch + 1) / 2 : 0, ch_end = eh ? nch : (nch + 1) / 2;
-        auto process = [&](const uint32_t (&rr)[16], int c0) {
-          if (!ri.valid) return;
-          if (EPI == VDA_EPI_LINEAR) {
-            const int col = col_base + c0;
-            if (col < p.N) {
-              float v[16];
+      if (EPI == VDA_EPI_TAIL) {   // block_n == N == 32: one dot product per row, thread = row (no staging)
+        const int r = q * 32 + lane;
+        bool valid;
+        long long out_row;
+        if (CONV) {
+          const int per_img = p.tiles_x * p.tiles_y;
+          const int img = m_blk / per_img;
+          const int rem = m_blk - img * per_img;
+          const int y = (rem / p.tiles_x) * p.bh + r / p.bw;
+          const int x = (rem % p.tiles_x) * p.bw + r % p.bw;
+          valid = (y < p.H) && (x < p.W);
+          out_row = (static_cast<long long>(img) * p.H + y) * p.W + x;
+        } else {
+          out_row = static_cast<long long>(m_blk) * BLOCK_M + r;
+          valid = out_row < p.M;
+        }
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        if (eh == 0) {
+          float acc = p.tail_b;
+          uint32_t rr[32];
+          tmem_ld32(t_row, rr);
+          tmem_ld_wait32(rr);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]);
-              epi_linear16<T>(p, ri, col, p.N - col, v);
-            }
-            return;
+          for (int i = 0; i < 32; ++i) {
+            const float h = fmaxf(__uint_as_float(rr[i]) + __ldg(p.bias + i), 0.f);
+            acc = fmaf(h, __ldg(p.tail_w + i), acc);
           }
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int col = col_base + c0 + 8 * g;
-            if (col < p.N) {
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[8 * g + i]);
-              const int kk = col / p.convt_co;
-              const int co = col - kk * p.convt_co;
-              const int ky = kk / p.convt_s, kx = kk - ky * p.convt_s;
-              float t[8];
-              load8f(p.bias + co, t);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += t[i];
-              const long long orow = ri.out_row + static_cast<long long>(ky) * (p.in_w * p.convt_s) + kx;
-              store8<T>(reinterpret_cast<T*>(p.out) + orow * p.ldo + co, v);
+          if (valid) reinterpret_cast<float*>(p.out)[out_row] = fmaxf(acc, 0.f);
+        }
+      } else {
+        // (output row, res1 row) of tile row r; output row -1 = outside the problem
+        auto row_info = [&](int r, int& o, int& rr) {
+          if (CONV) {
+            const int per_img = p.tiles_x * p.tiles_y;
+            const int img = m_blk / per_img;
+            const int rem = m_blk - img * per_img;
+            const int y = (rem / p.tiles_x) * p.bh + r / p.bw;
+            const int x = (rem % p.tiles_x) * p.bw + r % p.bw;
+            o = ((y < p.H) && (x < p.W)) ? (img * p.H + y) * p.W + x : -1;
+            rr = o;
+          } else {
+            const int m = m_blk * BLOCK_M + r;
+            o = m < p.M ? m : -1;
+            rr = m;
+            if (p.row_group > 0) {
+              o = m < p.M ? m + m / p.row_group + 1 : -1;
+              rr = m % p.row_group + 1;
+            }
+            if (EPI == VDA_EPI_CONVT && m < p.M) {
+              const int per_img = p.in_h * p.in_w;
+              const int img = m / per_img;
+              const int rem = m - img * per_img;
+              const int y = rem / p.in_w, x = rem - y * p.in_w;
+              // row index of output pixel (img, y*S, x*S) in the upsampled map
+              o = (img * p.in_h * p.convt_s + y * p.convt_s) * (p.in_w * p.convt_s) + x * p.convt_s;
             }
           }
         };
-        // software-pipelined TMEM drain: the load of chunk i+1 is in flight while chunk i is processed
-        uint32_t ra[16], rb[16];
-        if (ch_begin < ch_end) tmem_ld16(t_row + ch_begin * 16, ra);
-        for (int ch = ch_begin; ch < ch_end; ch += 2) {
-          tmem_ld_wait16(ra);
-          if (ch + 1 < ch_end) tmem_ld16(t_row + (ch + 1) * 16, rb);
-          process(ra, ch * 16);
-          if (ch + 1 < ch_end) {
-            tmem_ld_wait16(rb);
-            if (ch + 2 < ch_end) tmem_ld16(t_row + (ch + 2) * 16, ra);
-            process(rb, (ch + 1) * 16);
-          }
+        constexpr bool staged = STAGED;
+        int orow[8], rrow[8];     // staged: rows of this lane in the transposed (phase 2) passes
+        int o_row = -1, r_row = 0;   // direct: this thread's own row
+        if (staged) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) row_info(q * 32 + it * 4 + rsub, orow[it], rrow[it]);
+        } else {
+          row_info(q * 32 + lane, o_row, r_row);
         }
-      } else if (EPI == VDA_EPI_GEGLU) {
-        const int half = p.geglu_half;
-        const int nch = half >> 4;
-        const int ch_begin = eh ? (nch + 1) / 2 : 0, ch_end = eh ? nch : (nch + 1) / 2;
-        for (int c0 = ch_begin * 16; c0 < ch_end * 16; c0 += 16) {
-          uint32_t ra[16], rg[16];
-          tmem_ld16(t_row + c0, ra);
-          tmem_ld16(t_row + half + c0, rg);
-          tmem_ld_wait16(ra);
-          tmem_ld_wait16(rg);
-          if (ri.valid) {
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+
+        if ((EPI == VDA_EPI_LINEAR || EPI == VDA_EPI_CONVT) && !STAGED) {
+          // ---- direct path (16-bit operands only): thread = row, 16 columns per step, no shared-memory traffic
+          //      (the operand ring already uses ~3/4 of the smem bandwidth while the tensor pipe is busy) ----
+          const int nch = p.block_n >> 4;
+          const int ch_begin = eh ? (nch + 1) / 2 : 0, ch_end = eh ? nch : (nch + 1) / 2;
+          auto process = [&](const uint32_t (&rr)[16], int c0) {
+            const int col = col_base + c0;
+            if (o_row < 0 || col >= p.N) return;
+            const bool two = p.N - col > 8;      // N % 8 == 0: a 16-column chunk holds 8 or 16 valid columns
+            F4 v[4];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const int pc = col_base + c0 + 8 * g;          // packed column of `a`
-              if (pc < p.N) {
-                float ba[8], bg[8], v[8];
-                load8f(p.bias + pc, ba);
-                load8f(p.bias + pc + half, bg);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float a = __uint_as_float(ra[8 * g + i]) + ba[i];
-                  const float gt = __uint_as_float(rg[8 * g + i]) + bg[i];
-                  v[i] = a * gelu_erf(gt);
-                }
-                const int oc = n_blk * half + c0 + 8 * g;
-                store8<T>(reinterpret_cast<T*>(p.out) + ri.out_row * p.ldo + oc, v);
+            for (int i = 0; i < 4; ++i) {
+              v[i].a = make_float2(__uint_as_float(rr[4 * i]), __uint_as_float(rr[4 * i + 1]));
+              v[i].b = make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3]));
+            }
+            int co = col;
+            long long orow_l = o_row;
+            if (EPI == VDA_EPI_CONVT) {
+              const int kk = col / p.convt_co;
+              co = col - kk * p.convt_co;
+              const int ky = kk / p.convt_s, kx = kk - ky * p.convt_s;
+              orow_l += static_cast<long long>(ky) * (p.in_w * p.convt_s) + kx;
+            }
+            F4 r1[4], r2[4];
+            if (EPI == VDA_EPI_LINEAR) {   // all global loads before any store
+              if (p.res1) {
+                const T* r = reinterpret_cast<const T*>(p.res1) + r_row * p.ldr1 + col;
+                r1[0] = load4h<T>(r); r1[1] = load4h<T>(r + 4);
+                if (two) { r1[2] = load4h<T>(r + 8); r1[3] = load4h<T>(r + 12); }
+              }
+              if (p.res2) {
+                const T* r = reinterpret_cast<const T*>(p.res2) + orow_l * p.ldo + col;
+                r2[0] = load4h<T>(r); r2[1] = load4h<T>(r + 4);
+                if (two) { r2[2] = load4h<T>(r + 8); r2[3] = load4h<T>(r + 12); }
               }
             }
-          }
-        }
-      } else {  // VDA_EPI_TAIL: block_n == N == 32
-        if (eh == 0) {   // 32 columns only: one warp per quadrant does the whole row
-          float acc = p.tail_b;
-          uint32_t r0[16], r1[16];
-          tmem_ld16(t_row, r0);
-          tmem_ld16(t_row + 16, r1);
-          tmem_ld_wait16(r0);
-          tmem_ld_wait16(r1);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float h = fmaxf(__uint_as_float(r0[i]) + __ldg(p.bias + i), 0.f);
-            acc = fmaf(h, __ldg(p.tail_w + i), acc);
+            for (int i = 0; i < 4; ++i) {
+              if (i >= 2 && !two) break;
+              if (p.bias) v[i] = add4(v[i], load4f(p.bias + co + 4 * i));
+              if (EPI == VDA_EPI_LINEAR) {
+                if (p.gamma) v[i] = mul4(v[i], load4f(p.gamma + col + 4 * i));
+                if (p.act == VDA_ACT_GELU) v[i] = gelu4(v[i]);
+                else if (p.act == VDA_ACT_RELU) v[i] = relu4(v[i]);
+                if (p.res1) v[i] = add4(v[i], r1[i]);
+                if (p.res2) v[i] = add4(v[i], r2[i]);
+              }
+            }
+            T* o = reinterpret_cast<T*>(p.out) + orow_l * p.ldo + co;
+            auto st8 = [&](T* dst, const F4& x, const F4& y) {
+              uint4 u;
+              u.x = H16<T>::pack2(x.a.x, x.a.y); u.y = H16<T>::pack2(x.b.x, x.b.y);
+              u.z = H16<T>::pack2(y.a.x, y.a.y); u.w = H16<T>::pack2(y.b.x, y.b.y);
+              *reinterpret_cast<uint4*>(dst) = u;
+            };
+            st8(o, v[0], v[1]);
+            if (two) st8(o + 8, v[2], v[3]);
+            if (EPI == VDA_EPI_LINEAR && p.out_relu) {
+              T* orl = reinterpret_cast<T*>(p.out_relu) + orow_l * p.ldo + co;
+              st8(orl, relu4(v[0]), relu4(v[1]));
+              if (two) st8(orl + 8, relu4(v[2]), relu4(v[3]));
+            }
+          };
+          // software-pipelined TMEM drain: the load of chunk i+1 is in flight while chunk i is processed
+          uint32_t ra[16], rb[16];
+          if (ch_begin < ch_end) tmem_ld16(t_row + ch_begin * 16, ra);
+          for (int ch = ch_begin; ch < ch_end; ch += 2) {
+            tmem_ld_wait16(ra);
+            if (ch + 1 < ch_end) tmem_ld16(t_row + (ch + 1) * 16, rb);
+            process(ra, ch * 16);
+            if (ch + 1 < ch_end) {
+              tmem_ld_wait16(rb);
+              if (ch + 2 < ch_end) tmem_ld16(t_row + (ch + 2) * 16, ra);
+              process(rb, (ch + 1) * 16);
+            }
           }
+        } else if (EPI == VDA_EPI_LINEAR || EPI == VDA_EPI_CONVT) {
+          const int nch = p.block_n >> 4;                                  // 16-column units in the tile
+          const int c_begin = (eh ? (nch + 1) / 2 : 0) * 16;
+          const int c_end = (eh ? nch : (nch + 1) / 2) * 16;
+          for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            const bool wide = c0 + 32 <= c_end;                            // 32 columns, else the last 16
+            // ---- phase 1: accumulators (thread = row) -> swizzled staging tile ----
+            {
+              uint32_t rr[32];
+              if (wide) {
+                tmem_ld32(t_row + c0, rr);
+                tmem_ld_wait32(rr);
+              } else {
+                tmem_ld16(t_row + c0, *reinterpret_cast<uint32_t(*)[16]>(rr));
+                tmem_ld_wait16(*reinterpret_cast<uint32_t(*)[16]>(rr));
+              }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float h = fmaxf(__uint_as_float(r1[i]) + __ldg(p.bias + 16 + i), 0.f);
-            acc = fmaf(h, __ldg(p.tail_w + 16 + i), acc);
+              for (int c4 = 0; c4 < 8; ++c4)
+                if (wide || c4 < 4)
+                  sts128(stg + stg_off(lane, c4), rr[4 * c4], rr[4 * c4 + 1], rr[4 * c4 + 2], rr[4 * c4 + 3]);
+            }
+            __syncwarp();
+            // ---- phase 2: lane = 4 consecutive columns of 8 rows; coalesced residual loads and stores ----
+            const int col = col_base + c0 + 4 * cg;
+            const bool col_ok = col < p.N && (wide || cg < 4);
+            if (col_ok) {
+              F4 bias4, gamma4;
+              int co = col;
+              long long cshift = 0;     // CONVT: (ky * out_width + kx) rows
+              if (EPI == VDA_EPI_CONVT) {
+                const int kk = col / p.convt_co;
+                co = col - kk * p.convt_co;
+                const int ky = kk / p.convt_s, kx = kk - ky * p.convt_s;
+                cshift = static_cast<long long>(ky) * (p.in_w * p.convt_s) + kx;
+              }
+              if (p.bias) bias4 = load4f(p.bias + co);
+              if (p.gamma) gamma4 = load4f(p.gamma + col);
+              F4 r1[8], r2[8];
+              if (EPI == VDA_EPI_LINEAR) {
+                // every global load is issued before any store (out may alias res1)
+                if (p.res1) {
+#pragma unroll
+                  for (int it = 0; it < 8; ++it) {
+                    if (orow[it] >= 0) {
+                      if (p.res1_f32)
+                        r1[it] = load4f(reinterpret_cast<const float*>(p.res1) + rrow[it] * p.ldr1 + col);
+                      else
+                        r1[it] = load4h<T>(reinterpret_cast<const T*>(p.res1) + rrow[it] * p.ldr1 + col);
+                    }
+                  }
+                }
+                if (p.res2) {
+#pragma unroll
+                  for (int it = 0; it < 8; ++it)
+                    if (orow[it] >= 0) r2[it] = load4h<T>(reinterpret_cast<const T*>(p.res2) + orow[it] * p.ldo + col);
+                }
+              }
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                if (orow[it] < 0) continue;
+                F4 v = lds128(stg + stg_off(it * 4 + rsub, cg));
+                if (p.bias) v = add4(v, bias4);
+                if (EPI == VDA_EPI_LINEAR) {
+                  if (p.gamma) v = mul4(v, gamma4);
+                  if (p.act == VDA_ACT_GELU) v = gelu4(v);
+                  else if (p.act == VDA_ACT_RELU) v = relu4(v);
+                  if (p.res1) v = add4(v, r1[it]);
+                  if (p.res2) v = add4(v, r2[it]);
+                }
+                const long long o = (orow[it] + cshift) * p.ldo + co;
+                if (p.out_f32) store4f(reinterpret_cast<float*>(p.out) + o, v);
+                else store4h<T>(reinterpret_cast<T*>(p.out) + o, v);
+                if (EPI == VDA_EPI_LINEAR && p.out_relu) store4h<T>(reinterpret_cast<T*>(p.out_relu) + o, relu4(v));
+              }
+            }
+            __syncwarp();
           }
-          if (ri.valid) reinterpret_cast<float*>(p.out)[ri.out_row] = fmaxf(acc, 0.f);
+        } else {  // VDA_EPI_GEGLU: tile columns are [a(half) | g(half)]; out[:, j] = (a + ba) * gelu(g + bg)
+          const int half = p.geglu_half;
+          const int nch = half >> 4;
+          const int c_begin = (eh ? (nch + 1) / 2 : 0) * 16;
+          const int c_end = (eh ? nch : (nch + 1) / 2) * 16;
+          for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            const bool wide = c0 + 32 <= c_end;
+            const int pc = col_base + c0 + 4 * cg;                    // packed column of `a`
+            const bool col_ok = pc < p.N && (wide || cg < 4);
+            F4 gl[8];
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {                    // pass 0: gate columns, pass 1: value columns
+              {
+                uint32_t rr[32];
+                const uint32_t ta = t_row + (pass == 0 ? half : 0) + c0;
+                if (wide) {
+                  tmem_ld32(ta, rr);
+                  tmem_ld_wait32(rr);
+                } else {
+                  tmem_ld16(ta, *reinterpret_cast<uint32_t(*)[16]>(rr));
+                  tmem_ld_wait16(*reinterpret_cast<uint32_t(*)[16]>(rr));
+                }
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4)
+                  if (wide || c4 < 4)
+                    sts128(stg + stg_off(lane, c4), rr[4 * c4], rr[4 * c4 + 1], rr[4 * c4 + 2], rr[4 * c4 + 3]);
+              }
+              __syncwarp();
+              if (col_ok) {
+                const F4 b4 = load4f(p.bias + pc + (pass == 0 ? half : 0));
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  if (orow[it] < 0) continue;
+                  const F4 v = add4(lds128(stg + stg_off(it * 4 + rsub, cg)), b4);
+                  if (pass == 0) {
+                    gl[it] = gelu4(v);
+                  } else {
+                    const int oc = n_blk * half + c0 + 4 * cg;
+                    store4h<T>(reinterpret_cast<T*>(p.out) + static_cast<long long>(orow[it]) * p.ldo + oc,
+                               mul4(v, gl[it]));
+                  }
+                }
+              }
+              __syncwarp();
+            }
+          }
         }
       }
       tc_fence_before();
@@ -486,9 +591,9 @@ static int pick_block_n(int N, int tiles_m) {
   return bn;
 }
 
-template <typename T, int EPI, bool CONV>
+template <typename T, int EPI, bool CONV, bool STAGED>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, size_t smem, cudaStream_t st) {
-  auto kfn = gemm_kernel<T, EPI, CONV>;
+  auto kfn = gemm_kernel<T, EPI, CONV, STAGED>;
   static size_t attr_smem = 0;   // per instantiation: largest dynamic smem opted in so far
   if (smem > attr_smem) {
     VDA_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -506,17 +611,20 @@ static int dispatch(const vda_gemm_params* p, const CUtensorMap& tmA, const CUte
   const bool conv = p->a_mode == VDA_A_CONV3;
   switch (p->epilogue) {
     case VDA_EPI_LINEAR:
-      return conv ? launch<T, VDA_EPI_LINEAR, true>(tmA, tmB, d, smem, st)
-                  : launch<T, VDA_EPI_LINEAR, false>(tmA, tmB, d, smem, st);
+      if (d.staged)
+        return conv ? launch<T, VDA_EPI_LINEAR, true, true>(tmA, tmB, d, smem, st)
+                    : launch<T, VDA_EPI_LINEAR, false, true>(tmA, tmB, d, smem, st);
+      return conv ? launch<T, VDA_EPI_LINEAR, true, false>(tmA, tmB, d, smem, st)
+                  : launch<T, VDA_EPI_LINEAR, false, false>(tmA, tmB, d, smem, st);
     case VDA_EPI_GEGLU:
       VDA_CHECK(!conv, "GEGLU epilogue is only defined for plain GEMMs");
-      return launch<T, VDA_EPI_GEGLU, false>(tmA, tmB, d, smem, st);
+      return launch<T, VDA_EPI_GEGLU, false, true>(tmA, tmB, d, smem, st);
     case VDA_EPI_CONVT:
       VDA_CHECK(!conv, "CONVT epilogue is only defined for plain GEMMs");
-      return launch<T, VDA_EPI_CONVT, false>(tmA, tmB, d, smem, st);
+      return launch<T, VDA_EPI_CONVT, false, false>(tmA, tmB, d, smem, st);
     case VDA_EPI_TAIL:
-      return conv ? launch<T, VDA_EPI_TAIL, true>(tmA, tmB, d, smem, st)
-                  : launch<T, VDA_EPI_TAIL, false>(tmA, tmB, d, smem, st);
+      return conv ? launch<T, VDA_EPI_TAIL, true, false>(tmA, tmB, d, smem, st)
+                  : launch<T, VDA_EPI_TAIL, false, false>(tmA, tmB, d, smem, st);
   }
   set_error("unknown epilogue %d", p->epilogue);
   return 1;
@@ -600,10 +708,21 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
   d.stage_bytes = kABytes + static_cast<uint32_t>(d.block_n) * BLOCK_K * 2;
   // block_n*128 is a multiple of 2048 only when block_n % 16 == 0 -> every stage stays 1024-byte aligned
   d.stage_bytes = (d.stage_bytes + 1023u) & ~1023u;
-  int stages = static_cast<int>((227u * 1024u - 2048u) / d.stage_bytes);
+  // 227 KB per CTA: 1 KB alignment slack + static barriers, the epilogue staging tiles, the rest for the operand ring
+  // LINEAR epilogue variant (measured with tools/bench_gemm.py): the shared-memory transpose wins whenever the
+  // global traffic of the epilogue is stores only or fp32 (coalesced rows); with 16-bit residual operands the
+  // row-per-thread path (128-bit loads, no extra smem traffic next to the operand ring) is faster.
+  d.staged = (p->epilogue == VDA_EPI_GEGLU ||
+              (p->epilogue == VDA_EPI_LINEAR && !((p->res1 && !p->res1_f32) || p->res2))) ? 1 : 0;
+  if (p->epilogue == VDA_EPI_LINEAR) {   // debug hook (tools/bench_gemm.py): force the epilogue variant
+    static const char* force = getenv("VDA_GEMM_STAGED");
+    if (force && (force[0] == '0' || force[0] == '1')) d.staged = force[0] - '0';
+  }
+  const uint32_t staging = d.staged ? kStagingBytes : 0u;
+  int stages = static_cast<int>((227u * 1024u - 1024u - 512u - staging) / d.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   d.stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * d.stage_bytes + 1024;
+  const size_t smem = static_cast<size_t>(stages) * d.stage_bytes + staging + 1024;
   uint32_t cols = 32;
   while (cols < 2u * d.block_n) cols <<= 1;
   d.tmem_cols = cols;
