@@ -97,3 +97,17 @@ def test_full_size_window_vs_oracle(enc, dtype, tol):
     fin, rows, d, ref = stage_report(enc, 0, (1, 32, 3, 518, 518), 1234, dtype, oracle_device="cuda")
     assert (ref > 0).float().mean() > 0.99
     _check(dtype, *fin, f"{enc} 1x32x518x518")
+
+
+def test_sharded_driver_single_process_equals_plain():
+    """parallel.infer_video_depth_sharded without a process group is exactly infer_video_depth (N>1 logic is covered
+    on CPU with gloo in tests/test_parallel_cpu.py; tests/multi_gpu_check.py runs it under torchrun on N GPUs)."""
+    from video_depth_anything_b200.parallel import infer_video_depth_sharded
+    name = IVD[0]
+    c = MAN[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    m, _ = build_model(c["encoder"], c["seed"], torch.float16)
+    m.metric = c["mode"] == "identity"
+    a, _ = m.infer_video_depth(g["frames"], 24, input_size=c["input_size"], device="cuda")
+    b, _ = infer_video_depth_sharded(m, g["frames"], 24, input_size=c["input_size"])
+    assert np.array_equal(a, b)
