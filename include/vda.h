@@ -139,7 +139,9 @@ int vda_add_h16(const void* a, const void* b, void* out, int64_t n, int dtype, v
 
 /* Key-frame least squares (utils/util.py:40-62 with the all-ones mask of video_depth.py:230-232).
  * pred/target: fp32 [n] (two frames each).  scale_shift: fp32 [2] <- (s, t); identity if det == 0.
- * scratch: double [5] workspace. */
+ * scratch: double [4 * VDA_LSQ_MAX_PARTIALS] workspace (per-CTA partial sums, reduced in a fixed order so the
+ * result is bit-reproducible run to run and across GPU counts). */
+#define VDA_LSQ_MAX_PARTIALS 592
 int vda_lsq_scale_shift(const float* pred, const float* target, int64_t n, float* scale_shift, double* scratch,
                         void* stream);
 

@@ -280,7 +280,7 @@ def check_lsq_affine(hw, seed=0):
     pred = _rand((2, hw), seed).abs() + 0.1
     target = pred * 1.7 + 0.25 + _rand((2, hw), seed + 1, 0.01)
     ss = torch.zeros(2, device=DEV)
-    scratch = torch.zeros(8, device=DEV, dtype=torch.float64)
+    scratch = torch.zeros(4 * ops.LSQ_MAX_PARTIALS, device=DEV, dtype=torch.float64)
     ops.lsq_scale_shift(pred, target, ss, scratch)
     s_ref, t_ref = compute_scale_and_shift(pred.cpu().numpy().reshape(-1), target.cpu().numpy().reshape(-1))
     x = _rand((8, hw), seed + 2)

@@ -41,6 +41,31 @@ def run(frames, N, heads, dt, iters=10, check=True):
     print(f"attn {frames}x{N}x{heads} {dt}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s{msg}", flush=True)
 
 
+def run_temporal(T, hw, C, dt, iters=10):
+    g = torch.Generator().manual_seed(0)
+    qkv = torch.randn(T * hw, 3 * C, generator=g).cuda().to(dt)
+    out = torch.zeros(T * hw, C, device="cuda", dtype=dt)
+    ops.attention_temporal(qkv, out, T, hw, C)
+    torch.cuda.synchronize()
+    heads, dh = 8, C // 8
+    q, k, v = (qkv[:, i * C:(i + 1) * C].float().reshape(T, hw, heads, dh).permute(1, 2, 0, 3) for i in range(3))
+    ref = F.scaled_dot_product_attention(q, k, v).permute(2, 0, 1, 3).reshape(T * hw, C)
+    err = (out.float() - ref).abs().max().item()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        ops.attention_temporal(qkv, out, T, hw, C)
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ms = sorted(ts)[len(ts) // 2]
+    gb = 4.0 * T * hw * C * 2 / 1e9
+    print(f"temporal attn T={T} hw={hw} C={C} {dt}: {ms * 1e3:.1f} us  {gb / ms * 1e3:.0f} GB/s (q,k,v,o)  max abs err {err:.3e}", flush=True)
+
+
 def timing_report(steps):
     """Per-phase cycle sums of CTA 0's softmax warps (only in a -DVDA_SA_TIMING build)."""
     import ctypes as C
@@ -60,6 +85,11 @@ def timing_report(steps):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "temporal":
+        for hw, C in ((1369, 1024), (361, 1024), (1369, 256), (5476, 256), (1369, 192), (361, 384), (5476, 64)):
+            run_temporal(32, hw, C, torch.bfloat16)
+        run_temporal(8, 100, 256, torch.float16)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "timing":
         run(8, 1370, 16, torch.bfloat16, iters=1, check=False)
         # CTA 0 of 148 handles items 0,148,...: 768 items -> 6 items (5 full + 1 half) -> 66 / 55 steps

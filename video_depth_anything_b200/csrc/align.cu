@@ -1,5 +1,6 @@
 // Key-frame scale/shift alignment of the long-video driver (video_depth.py:216-252, utils/util.py:40-74) on device:
-// a one-pass 5-sum reduction (warp shuffles, one double atomic per CTA per sum), a tiny solve kernel that keeps
+// a one-pass 4-sum reduction (warp shuffles, per-CTA double partials summed in a fixed order: bit-reproducible
+// run to run, no atomics), a tiny solve kernel that keeps
 // (scale, shift) in device memory (no host round trip), and a fused affine + clamp + cross-fade kernel.
 #include "../../include/vda.h"
 #include "common.cuh"
@@ -44,11 +45,16 @@ __global__ void __launch_bounds__(256) lsq_sums_kernel(const float* __restrict__
   if (threadIdx.x < 4) {
     double a = 0.0;
     for (int w = 0; w < (blockDim.x >> 5); ++w) a += sh[threadIdx.x][w];
-    atomicAdd(&sums[threadIdx.x], a);
+    sums[static_cast<size_t>(blockIdx.x) * 4 + threadIdx.x] = a;      // per-CTA partial, reduced by the solve kernel
   }
 }
 
-__global__ void lsq_solve_kernel(const double* __restrict__ sums, long long n, float* __restrict__ scale_shift) {
+__global__ void lsq_solve_kernel(const double* __restrict__ partials, int n_part, long long n,
+                                 float* __restrict__ scale_shift) {
+  double sums[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = 0; i < n_part; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sums[k] += partials[static_cast<size_t>(i) * 4 + k];
   // utils/util.py:51-62 evaluated on float32 sums like the reference (np.float32 scalars)
   const float a00 = static_cast<float>(sums[0]), a01 = static_cast<float>(sums[1]), a11 = static_cast<float>(n);
   const float b0 = static_cast<float>(sums[2]), b1 = static_cast<float>(sums[3]);
@@ -89,12 +95,11 @@ extern "C" int vda_lsq_scale_shift(const float* pred, const float* target, int64
   VDA_CHECK((reinterpret_cast<uintptr_t>(pred) & 15) == 0 && (reinterpret_cast<uintptr_t>(target) & 15) == 0,
             "lsq: inputs must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  VDA_CUDA(cudaMemsetAsync(scratch, 0, 5 * sizeof(double), st));
   long long g = (n / 4 + 255) / 256;
-  if (g > 148 * 4) g = 148 * 4;
+  if (g > VDA_LSQ_MAX_PARTIALS) g = VDA_LSQ_MAX_PARTIALS;
   if (g < 1) g = 1;
   lsq_sums_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(pred, target, n, scratch);
-  lsq_solve_kernel<<<1, 1, 0, st>>>(scratch, n, scale_shift);
+  lsq_solve_kernel<<<1, 1, 0, st>>>(scratch, static_cast<int>(g), n, scale_shift);
   VDA_CUDA(cudaGetLastError());
   return 0;
 }

@@ -12,6 +12,7 @@ from . import _lib
 from ._lib import (A_CONV3, A_PLAIN, ACT_GELU, ACT_NONE, ACT_RELU, EPI_CONVT, EPI_GEGLU, EPI_LINEAR, EPI_TAIL,
                    GemmParams, VDA_BF16, VDA_FP16, check)
 
+LSQ_MAX_PARTIALS = 592   # include/vda.h VDA_LSQ_MAX_PARTIALS
 LAUNCHES = 0   # number of libvda kernel launches issued (bench.py reports it as gpu_launches)
 PROFILE = None  # when a list: every op appends (name, info dict, start_event, end_event)   [bench.py / tools]
 _INFO = {}
@@ -200,7 +201,7 @@ def add_h16(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor):
 def lsq_scale_shift(pred: torch.Tensor, target: torch.Tensor, scale_shift: torch.Tensor, scratch: torch.Tensor):
     lib = _lib.load()
     assert pred.is_contiguous() and target.is_contiguous() and pred.numel() == target.numel()
-    assert scratch.dtype == torch.float64 and scratch.numel() >= 5
+    assert scratch.dtype == torch.float64 and scratch.numel() >= 4 * LSQ_MAX_PARTIALS
     check(lib.vda_lsq_scale_shift(_p(pred), _p(target), pred.numel(), _p(scale_shift), _p(scratch), _stream()))
     _count(2)
 

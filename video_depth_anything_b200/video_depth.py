@@ -148,7 +148,7 @@ class WindowAligner:
         self.filled = 0
         self.ref = None                      # [2,h0,w0]: (ref_align[0], ref_align[1])
         self.ss = torch.tensor([1.0, 0.0], dtype=torch.float32, device=device)
-        self.scratch = torch.zeros(8, dtype=torch.float64, device=device)
+        self.scratch = torch.zeros(4 * ops.LSQ_MAX_PARTIALS, dtype=torch.float64, device=device)
         step = 1.0 / (INTERP_LEN - 1)
         self.blend_w = torch.tensor([0.0] + [i * step for i in range(1, INTERP_LEN - 1)] + [1.0],
                                     dtype=torch.float32, device=device)
