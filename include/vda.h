@@ -99,7 +99,9 @@ int vda_layernorm(const void* in, int in_f32, void* out, const float* w, const f
                   void* stream);
 
 /* GroupNorm(32, C, eps) per frame over an NHWC h16 tensor [frames, hw, C] (motion_module.py:84,110).
- * stats: fp32 scratch [frames*groups*2]. */
+ * stats: fp32 scratch of VDA_GN_STATS_FLOATS(frames, groups) floats (per-slab partial sums + per-frame totals;
+ * no atomics, so the result is bit-reproducible). */
+#define VDA_GN_STATS_FLOATS(frames, groups) ((592 + 2 * (frames)) * (groups) * 2)
 int vda_groupnorm(const void* in, void* out, const float* w, const float* b, float eps, int frames, int hw, int C,
                   int groups, float* stats, int dtype, void* stream);
 

@@ -65,6 +65,16 @@ def conv(name, n, H, W, ci, co, **kw):
 
 if __name__ == "__main__":
     M = 43840
+    if len(sys.argv) > 1 and sys.argv[1] == "prof":     # one launch per shape, for ncu
+        def once(fn, iters=1):
+            fn()
+            torch.cuda.synchronize()
+            return 1.0
+        timeit = once
+        plain("proj (+ls, fp32 residual in place)", M, 1024, 1024, out_f32=True, res_f32=True)
+        plain("fc1 + GELU", M, 4096, 1024, act=ACT_GELU)
+        plain("fc2 (+ls, fp32 residual in place)", M, 1024, 4096, out_f32=True, res_f32=True)
+        sys.exit(0)
     plain("qkv", M, 3072, 1024)
     plain("proj (+ls, fp32 residual in place)", M, 1024, 1024, out_f32=True, res_f32=True)
     plain("fc1 + GELU", M, 4096, 1024, act=ACT_GELU)

@@ -125,7 +125,7 @@ __device__ __forceinline__ F4 lds128(uint32_t addr) {
 constexpr uint32_t kStageTile = 32 * 32 * 4;            // per-warp epilogue staging tile (bytes)
 constexpr uint32_t kStagingBytes = kEpiWarps * kStageTile;
 
-template <typename T, int EPI, bool CONV, bool STAGED>
+template <typename T, int EPI, bool CONV, bool STAGED, int SPEC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
@@ -305,6 +305,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
         constexpr bool staged = STAGED;
+        if (EPI == VDA_EPI_LINEAR && (p.res1 || p.res2)) {
+          // pull the residual rows of this CTA's NEXT tile towards L2 now: its epilogue then reads them at L2
+          // latency instead of queueing behind HBM (the epilogue is a dependent load -> math -> store chain)
+          const int nxt = tile + gridDim.x;
+          if (nxt < p.num_tiles) {
+            const int n_blk2 = nxt % p.tiles_n, m_blk_save = m_blk;
+            (void)m_blk_save;
+            int o2, r2i;
+            {
+              const int m_blk2 = nxt / p.tiles_n;
+              const int r = q * 32 + lane;
+              if (CONV) {
+                const int per_img = p.tiles_x * p.tiles_y;
+                const int img = m_blk2 / per_img;
+                const int rem = m_blk2 - img * per_img;
+                const int y = (rem / p.tiles_x) * p.bh + r / p.bw;
+                const int x = (rem % p.tiles_x) * p.bw + r % p.bw;
+                o2 = ((y < p.H) && (x < p.W)) ? (img * p.H + y) * p.W + x : -1;
+                r2i = o2;
+              } else {
+                const int m = m_blk2 * BLOCK_M + r;
+                o2 = m < p.M ? m : -1;
+                r2i = m;
+                if (p.row_group > 0) {
+                  o2 = m < p.M ? m + m / p.row_group + 1 : -1;
+                  r2i = m % p.row_group + 1;
+                }
+              }
+            }
+            if (o2 >= 0) {
+              const int nch = p.block_n >> 4;
+              const int c_lo = n_blk2 * p.block_n + (eh ? (nch + 1) / 2 : 0) * 16;
+              int c_hi = n_blk2 * p.block_n + (eh ? nch : (nch + 1) / 2) * 16;
+              if (c_hi > p.N) c_hi = p.N;
+              if (p.res1) {
+                const int esz = p.res1_f32 ? 4 : 2;
+                const char* base = reinterpret_cast<const char*>(p.res1) + (r2i * p.ldr1 + c_lo) * esz;
+                for (int off = 0; off < (c_hi - c_lo) * esz; off += 128) prefetch_l2(base + off);
+              }
+              if (p.res2) {
+                const char* base = reinterpret_cast<const char*>(p.res2) + (o2 * p.ldo + c_lo) * 2;
+                for (int off = 0; off < (c_hi - c_lo) * 2; off += 128) prefetch_l2(base + off);
+              }
+            }
+          }
+        }
         int orow[8], rrow[8];     // staged: rows of this lane in the transposed (phase 2) passes
         int o_row = -1, r_row = 0;   // direct: this thread's own row
         if (staged) {
@@ -313,8 +359,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         } else {
           row_info(q * 32 + lane, o_row, r_row);
         }
-        mbar_wait(&tfull_bar[as], aphase);
-        tc_fence_after();
+        if (!(EPI == VDA_EPI_LINEAR && STAGED)) {   // (the staged LINEAR path first issues its residual loads)
+          mbar_wait(&tfull_bar[as], aphase);
+          tc_fence_after();
+        }
 
         if ((EPI == VDA_EPI_LINEAR || EPI == VDA_EPI_CONVT) && !STAGED) {
           // ---- direct path (16-bit operands only): thread = row, 16 columns per step, no shared-memory traffic
@@ -392,10 +440,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               process(rb, (ch + 1) * 16);
             }
           }
-        } else if (EPI == VDA_EPI_LINEAR || EPI == VDA_EPI_CONVT) {
+        } else if (EPI == VDA_EPI_LINEAR) {
+          // ---- staged path: fp32 residual (optional) / fp32 or 16-bit output, no 16-bit residuals ----
+          // SPEC folds the run-time epilogue flags of the three hot encoder GEMMs at compile time (the generic
+          // version spends more instructions on flag tests, uniform loads and branches than on arithmetic):
+          //   1: bias -> 16 bit (qkv)   2: bias, GELU -> 16 bit (fc1)   3: bias, LayerScale, fp32 residual -> fp32 (proj, fc2)
+          const bool has_bias = SPEC != 0 ? true : p.bias != nullptr;
+          const bool has_gamma = SPEC != 0 ? SPEC == 3 : p.gamma != nullptr;
+          const int act = SPEC != 0 ? (SPEC == 2 ? VDA_ACT_GELU : VDA_ACT_NONE) : p.act;
+          const bool has_res = SPEC != 0 ? SPEC == 3 : (p.res1 != nullptr && p.res1_f32);
+          const bool out_f32 = SPEC != 0 ? SPEC == 3 : p.out_f32 != 0;
+          const bool relu_copy = SPEC != 0 ? false : p.out_relu != nullptr;
           const int nch = p.block_n >> 4;                                  // 16-column units in the tile
           const int c_begin = (eh ? (nch + 1) / 2 : 0) * 16;
           const int c_end = (eh ? nch : (nch + 1) / 2) * 16;
+          // per-row base pointers (rows of this lane in the transposed passes), once per tile
+          const float* rbase[8];
+          char* obase[8];
+          bool all_rows = true;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            rbase[it] = reinterpret_cast<const float*>(p.res1) + static_cast<long long>(rrow[it]) * p.ldr1;
+            obase[it] = reinterpret_cast<char*>(p.out) + static_cast<long long>(orow[it]) * p.ldo * (out_f32 ? 4 : 2);
+            all_rows = all_rows && orow[it] >= 0;
+          }
+          // residual row segments are loaded one chunk ahead (the first one before the accumulator is ready), so
+          // their HBM/L2 latency hides behind the TMEM drain and the math of the previous chunk
+          F4 rnxt[8];
+          auto load_res = [&](int c0) {
+            const int col = col_base + c0 + 4 * cg;
+            const bool ok = col < p.N && (c0 + 32 <= c_end || cg < 4);
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (ok && orow[it] >= 0) rnxt[it] = load4f(rbase[it] + col);
+          };
+          if (has_res && c_begin < c_end) load_res(c_begin);
+          mbar_wait(&tfull_bar[as], aphase);
+          tc_fence_after();
           for (int c0 = c_begin; c0 < c_end; c0 += 32) {
             const bool wide = c0 + 32 <= c_end;                            // 32 columns, else the last 16
             // ---- phase 1: accumulators (thread = row) -> swizzled staging tile ----
@@ -414,57 +495,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   sts128(stg + stg_off(lane, c4), rr[4 * c4], rr[4 * c4 + 1], rr[4 * c4 + 2], rr[4 * c4 + 3]);
             }
             __syncwarp();
-            // ---- phase 2: lane = 4 consecutive columns of 8 rows; coalesced residual loads and stores ----
+            // ---- phase 2: lane = 4 consecutive columns of 8 rows; coalesced row segments ----
             const int col = col_base + c0 + 4 * cg;
             const bool col_ok = col < p.N && (wide || cg < 4);
+            F4 v[8];
             if (col_ok) {
-              F4 bias4, gamma4;
-              int co = col;
-              long long cshift = 0;     // CONVT: (ky * out_width + kx) rows
-              if (EPI == VDA_EPI_CONVT) {
-                const int kk = col / p.convt_co;
-                co = col - kk * p.convt_co;
-                const int ky = kk / p.convt_s, kx = kk - ky * p.convt_s;
-                cshift = static_cast<long long>(ky) * (p.in_w * p.convt_s) + kx;
-              }
-              if (p.bias) bias4 = load4f(p.bias + co);
-              if (p.gamma) gamma4 = load4f(p.gamma + col);
-              F4 r1[8], r2[8];
-              if (EPI == VDA_EPI_LINEAR) {
-                // every global load is issued before any store (out may alias res1)
-                if (p.res1) {
+              // loads, math and stores in separate unrolled passes: the 16 independent packed chains of a lane
+              // are interleaved by the scheduler (the GELU chain alone is ~100 cycles deep)
 #pragma unroll
-                  for (int it = 0; it < 8; ++it) {
-                    if (orow[it] >= 0) {
-                      if (p.res1_f32)
-                        r1[it] = load4f(reinterpret_cast<const float*>(p.res1) + rrow[it] * p.ldr1 + col);
-                      else
-                        r1[it] = load4h<T>(reinterpret_cast<const T*>(p.res1) + rrow[it] * p.ldr1 + col);
-                    }
-                  }
-                }
-                if (p.res2) {
+              for (int it = 0; it < 8; ++it) v[it] = lds128(stg + stg_off(it * 4 + rsub, cg));
+              if (has_bias) {
+                const F4 bias4 = load4f(p.bias + col);
 #pragma unroll
-                  for (int it = 0; it < 8; ++it)
-                    if (orow[it] >= 0) r2[it] = load4h<T>(reinterpret_cast<const T*>(p.res2) + orow[it] * p.ldo + col);
-                }
+                for (int it = 0; it < 8; ++it) v[it] = add4(v[it], bias4);
               }
+              if (has_gamma) {
+                const F4 gamma4 = load4f(p.gamma + col);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) v[it] = mul4(v[it], gamma4);
+              }
+              if (act == VDA_ACT_GELU) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) v[it] = gelu4(v[it]);
+              } else if (act == VDA_ACT_RELU) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) v[it] = relu4(v[it]);
+              }
+              if (has_res) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) v[it] = add4(v[it], rnxt[it]);
+              }
+            }
+            if (has_res && c0 + 32 < c_end) load_res(c0 + 32);   // next chunk's residual, consumed one iteration later
+            if (col_ok) {
+              const int cbyte = col * (out_f32 ? 4 : 2);
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
-                if (orow[it] < 0) continue;
-                F4 v = lds128(stg + stg_off(it * 4 + rsub, cg));
-                if (p.bias) v = add4(v, bias4);
-                if (EPI == VDA_EPI_LINEAR) {
-                  if (p.gamma) v = mul4(v, gamma4);
-                  if (p.act == VDA_ACT_GELU) v = gelu4(v);
-                  else if (p.act == VDA_ACT_RELU) v = relu4(v);
-                  if (p.res1) v = add4(v, r1[it]);
-                  if (p.res2) v = add4(v, r2[it]);
-                }
-                const long long o = (orow[it] + cshift) * p.ldo + co;
-                if (p.out_f32) store4f(reinterpret_cast<float*>(p.out) + o, v);
-                else store4h<T>(reinterpret_cast<T*>(p.out) + o, v);
-                if (EPI == VDA_EPI_LINEAR && p.out_relu) store4h<T>(reinterpret_cast<T*>(p.out_relu) + o, relu4(v));
+                if (!all_rows && orow[it] < 0) continue;
+                if (out_f32) store4f(reinterpret_cast<float*>(obase[it] + cbyte), v[it]);
+                else store4h<T>(reinterpret_cast<T*>(obase[it] + cbyte), v[it]);
+                if (relu_copy)
+                  store4h<T>(reinterpret_cast<T*>(p.out_relu) + static_cast<long long>(orow[it]) * p.ldo + col, relu4(v[it]));
               }
             }
             __syncwarp();
@@ -499,17 +570,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               __syncwarp();
               if (col_ok) {
                 const F4 b4 = load4f(p.bias + pc + (pass == 0 ? half : 0));
+                F4 v[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) v[it] = lds128(stg + stg_off(it * 4 + rsub, cg));
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
-                  if (orow[it] < 0) continue;
-                  const F4 v = add4(lds128(stg + stg_off(it * 4 + rsub, cg)), b4);
-                  if (pass == 0) {
-                    gl[it] = gelu4(v);
-                  } else {
-                    const int oc = n_blk * half + c0 + 4 * cg;
-                    store4h<T>(reinterpret_cast<T*>(p.out) + static_cast<long long>(orow[it]) * p.ldo + oc,
-                               mul4(v, gl[it]));
-                  }
+                  v[it] = add4(v[it], b4);
+                  if (pass == 0) gl[it] = gelu4(v[it]);
+                  else v[it] = mul4(v[it], gl[it]);
+                }
+                if (pass == 1) {
+                  const int oc = n_blk * half + c0 + 4 * cg;
+#pragma unroll
+                  for (int it = 0; it < 8; ++it)
+                    if (orow[it] >= 0)
+                      store4h<T>(reinterpret_cast<T*>(p.out) + static_cast<long long>(orow[it]) * p.ldo + oc, v[it]);
                 }
               }
               __syncwarp();
@@ -591,9 +666,9 @@ static int pick_block_n(int N, int tiles_m) {
   return bn;
 }
 
-template <typename T, int EPI, bool CONV, bool STAGED>
+template <typename T, int EPI, bool CONV, bool STAGED, int SPEC = 0>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, size_t smem, cudaStream_t st) {
-  auto kfn = gemm_kernel<T, EPI, CONV, STAGED>;
+  auto kfn = gemm_kernel<T, EPI, CONV, STAGED, SPEC>;
   static size_t attr_smem = 0;   // per instantiation: largest dynamic smem opted in so far
   if (smem > attr_smem) {
     VDA_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -611,6 +686,16 @@ static int dispatch(const vda_gemm_params* p, const CUtensorMap& tmA, const CUte
   const bool conv = p->a_mode == VDA_A_CONV3;
   switch (p->epilogue) {
     case VDA_EPI_LINEAR:
+      if (d.staged && !conv) {
+        // compile-time specialisations of the hot encoder epilogues (see SPEC in the kernel)
+        const bool plain16 = p->bias && !p->res1 && !p->res2 && !p->out_f32 && !p->out_relu && !p->gamma &&
+                             p->row_group == 0;
+        if (plain16 && p->act == VDA_ACT_NONE) return launch<T, VDA_EPI_LINEAR, false, true, 1>(tmA, tmB, d, smem, st);
+        if (plain16 && p->act == VDA_ACT_GELU) return launch<T, VDA_EPI_LINEAR, false, true, 2>(tmA, tmB, d, smem, st);
+        if (p->bias && p->gamma && p->res1 && p->res1_f32 && !p->res2 && p->out_f32 && !p->out_relu &&
+            p->act == VDA_ACT_NONE && p->row_group == 0)
+          return launch<T, VDA_EPI_LINEAR, false, true, 3>(tmA, tmB, d, smem, st);
+      }
       if (d.staged)
         return conv ? launch<T, VDA_EPI_LINEAR, true, true>(tmA, tmB, d, smem, st)
                     : launch<T, VDA_EPI_LINEAR, false, true>(tmA, tmB, d, smem, st);

@@ -1,5 +1,5 @@
 // Bandwidth-bound normalisation kernels: LayerNorm (warp per row, fp32 statistics, 128-bit accesses) and
-// GroupNorm over NHWC activations (two-pass: partial sums with one atomic per CTA per group, then apply).
+// GroupNorm over NHWC activations (per-slab partial sums, fixed-order reduction, then apply; no atomics).
 #include "../../include/vda.h"
 #include "common.cuh"
 
@@ -77,21 +77,21 @@ layernorm_kernel(const void* __restrict__ in, T* __restrict__ out, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm over [frames, hw, C] (NHWC).  Pass 1: every CTA reduces a slab of pixels of one frame to
-// per-group (sum, sumsq) and adds them with one atomic per group.  Pass 2: normalise + affine.
+// GroupNorm over [frames, hw, C] (NHWC).  Pass 1: every CTA reduces a slab of pixels of one frame to per-group
+// (sum, sumsq) partials; pass 1b sums the slabs of a frame in a fixed order (no atomics anywhere: results are
+// bit-reproducible run to run); pass 2: normalise + affine.
+// stats layout: partials [frames][slabs][groups][2], then totals [frames][groups][2].
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-groupnorm_stats_kernel(const T* __restrict__ in, float* __restrict__ stats, int hw, int C, int groups,
+groupnorm_stats_kernel(const T* __restrict__ in, float* __restrict__ partials, int hw, int C, int groups,
                        int pix_per_cta) {
   // blockDim.x is a multiple of vecs = C/8, so a thread always visits the same 8-channel column and can
-  // keep its four channel-pair partial sums in registers; one shared-memory flush per thread at the end.
-  __shared__ float s_sum[64], s_sq[64];
+  // keep its four channel-pair partial sums in registers.
+  __shared__ float sh_s[256][4], sh_q[256][4];
   const int frame = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(p0 + pix_per_cta, hw);
-  if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
   const int cpg = C / groups;
   const int vecs = C >> 3;
   const long long total = static_cast<long long>(p1 - p0) * vecs;
@@ -107,18 +107,38 @@ groupnorm_stats_kernel(const T* __restrict__ in, float* __restrict__ stats, int 
       q[i] += f.x * f.x + f.y * f.y;
     }
   }
-  const int c0 = (threadIdx.x % vecs) * 8;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int g = (c0 + 2 * i) / cpg;       // cpg is even: a channel pair never straddles groups
-    atomicAdd(&s_sum[g], s[i]);
-    atomicAdd(&s_sq[g], q[i]);
-  }
+  for (int i = 0; i < 4; ++i) { sh_s[threadIdx.x][i] = s[i]; sh_q[threadIdx.x][i] = q[i]; }
   __syncthreads();
   if (threadIdx.x < groups) {
-    atomicAdd(&stats[(frame * groups + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
-    atomicAdd(&stats[(frame * groups + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+    // thread g sums, in thread order, every channel pair that belongs to group g (cpg is even: a pair never
+    // straddles groups)
+    const int g = threadIdx.x;
+    float ts = 0.f, tq = 0.f;
+    for (int t = 0; t < static_cast<int>(blockDim.x); ++t) {
+      const int c0 = (t % vecs) * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if ((c0 + 2 * i) / cpg == g) { ts += sh_s[t][i]; tq += sh_q[t][i]; }
+    }
+    float* dst = partials + ((static_cast<size_t>(frame) * gridDim.x + blockIdx.x) * groups + g) * 2;
+    dst[0] = ts;
+    dst[1] = tq;
   }
+}
+
+__global__ void groupnorm_reduce_kernel(const float* __restrict__ partials, float* __restrict__ totals, int slabs,
+                                        int groups) {
+  const int frame = blockIdx.x, g = threadIdx.x;
+  if (g >= groups) return;
+  float ts = 0.f, tq = 0.f;
+  for (int sl = 0; sl < slabs; ++sl) {
+    const float* src = partials + ((static_cast<size_t>(frame) * slabs + sl) * groups + g) * 2;
+    ts += src[0];
+    tq += src[1];
+  }
+  totals[(frame * groups + g) * 2] = ts;
+  totals[(frame * groups + g) * 2 + 1] = tq;
 }
 
 template <typename T>
@@ -187,23 +207,26 @@ extern "C" int vda_groupnorm(const void* in, void* out, const float* w, const fl
   VDA_CHECK(vecs <= 256, "GroupNorm: C (%d) too large", C);
   const int sthreads = (256 / vecs) * vecs;   // multiple of vecs (see groupnorm_stats_kernel)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  VDA_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * frames * groups * 2, st));
   // ~ 4 CTAs per SM worth of slabs per launch
   int slabs = (148 * 4 + frames - 1) / frames;
   if (slabs < 1) slabs = 1;
   int pix_per_cta = (hw + slabs - 1) / slabs;
   if (pix_per_cta < 8) pix_per_cta = 8;
-  dim3 grid((hw + pix_per_cta - 1) / pix_per_cta, frames);
+  slabs = (hw + pix_per_cta - 1) / pix_per_cta;
+  dim3 grid(slabs, frames);
+  float* totals = stats + static_cast<size_t>(frames) * slabs * groups * 2;   // fits VDA_GN_STATS_FLOATS
   const long long total = static_cast<long long>(frames) * hw * (C / 8);
   unsigned g2 = static_cast<unsigned>((total + 255) / 256);
   if (g2 > 148u * 16u) g2 = 148u * 16u;
   if (dtype == VDA_BF16) {
     groupnorm_stats_kernel<__nv_bfloat16><<<grid, sthreads, 0, st>>>(static_cast<const __nv_bfloat16*>(in), stats, hw, C, groups, pix_per_cta);
+    groupnorm_reduce_kernel<<<frames, 64, 0, st>>>(stats, totals, slabs, groups);
     groupnorm_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out),
-                                                              stats, w, b, eps, frames, hw, C, groups);
+                                                              totals, w, b, eps, frames, hw, C, groups);
   } else {
     groupnorm_stats_kernel<__half><<<grid, sthreads, 0, st>>>(static_cast<const __half*>(in), stats, hw, C, groups, pix_per_cta);
-    groupnorm_apply_kernel<__half><<<g2, 256, 0, st>>>(static_cast<const __half*>(in), static_cast<__half*>(out), stats, w, b,
+    groupnorm_reduce_kernel<<<frames, 64, 0, st>>>(stats, totals, slabs, groups);
+    groupnorm_apply_kernel<__half><<<g2, 256, 0, st>>>(static_cast<const __half*>(in), static_cast<__half*>(out), totals, w, b,
                                                        eps, frames, hw, C, groups);
   }
   VDA_CUDA(cudaGetLastError());

@@ -113,10 +113,10 @@ def groupnorm(x: torch.Tensor, w, b, eps: float, out: torch.Tensor, frames: int,
     """nn.GroupNorm(groups, C) per frame over NHWC h16 [frames, hw, C]."""
     lib = _lib.load()
     Cc = x.shape[-1]
-    stats = torch.empty(frames * groups * 2, dtype=torch.float32, device=x.device)
+    stats = torch.empty((592 + 2 * frames) * groups * 2, dtype=torch.float32, device=x.device)   # VDA_GN_STATS_FLOATS
     check(lib.vda_groupnorm(_p(x), _p(out), _p(w), _p(b), eps, frames, hw, Cc, groups, _p(stats), dt_code(x.dtype),
                             _stream()))
-    _count(2)
+    _count(3)
     return out
 
 
