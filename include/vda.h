@@ -133,6 +133,13 @@ int vda_im2col3x3_s2(const void* in, void* out, int n, int H, int W, int C, int 
 int vda_bilinear_nhwc(const void* in, void* out, int n, int ih, int iw, int oh, int ow, int C, int dtype,
                       void* stream);
 
+/* Fused depth-head tail (dpt_temporal.py:94-100, dpt.py:118-124): bilinear (align_corners=True) upsample of the
+ * output_conv1 map to (OH, OW), 3x3 conv C -> 32 (+bias, ReLU), 1x1 conv 32 -> 1 (+bias, ReLU), one kernel; the
+ * upsampled map never exists in memory.  in: h16 NHWC [n, IH, IW, C] (C = 64 or 128), w: h16 [32, 9*C] with
+ * K = (ky*3+kx)*C + ci, bias/w2: fp32 [32], out: fp32 [n, OH, OW]. */
+int vda_tail_fused(const void* in, const void* w, const float* bias, const float* w2, float b2, float* out, int n,
+                   int IH, int IW, int OH, int OW, int C, int dtype, void* stream);
+
 /* bilinear, align_corners=True, single-channel fp32 [n,ih,iw] -> [n,oh,ow] (video_depth.py:162,208) */
 int vda_bilinear_f32(const float* in, float* out, int n, int ih, int iw, int oh, int ow, void* stream);
 

@@ -162,6 +162,26 @@ def check_conv_tail(n, H, W, ci, dt, seed=0):
     return _err(out.reshape(ref.shape), ref), _tol(ref, dt) * 4
 
 
+def check_tail_fused(n, ih, iw, oh, ow, ci, dt, seed=0):
+    """bilinear(align_corners) upsample + 3x3 conv + ReLU + 1x1 + ReLU in one kernel vs the fp32 torch ops (the
+    reference rounds the upsampled map to 16 bit too: F.interpolate runs under autocast, dpt_temporal.py:94-100)."""
+    x = _rand((n, ci, ih, iw), seed, 1.0, dt)
+    w1 = _rand((32, ci, 3, 3), seed + 1, 1.0 / math.sqrt(9 * ci), dt)
+    b1 = _rand((32,), seed + 2, 0.1)
+    w2 = _rand((32,), seed + 3, 0.2).abs()
+    b2 = 0.05
+    up = F.interpolate(x.float(), size=(oh, ow), mode="bilinear", align_corners=True).to(dt).float()
+    h = F.relu(F.conv2d(up, w1.float(), b1, padding=1))
+    ref = F.relu((h * w2.view(1, 32, 1, 1)).sum(1) + b2)
+    from video_depth_anything_b200.engine import pack_conv3x3
+    wp = pack_conv3x3(w1, ci, 32)
+    a = x.permute(0, 2, 3, 1).contiguous()
+    out = torch.full((n, oh, ow), -1.0, device=DEV, dtype=torch.float32)
+    ops.tail_fused(a, wp, b1, w2, b2, out, n, ih, iw, oh, ow, ci)
+    torch.cuda.synchronize()
+    return _err(out, ref), _tol(ref, dt) * 4
+
+
 # ------------------------------------------------------------------------------------------------ others
 def check_layernorm(rows, C, dt, in_f32=True, drop_group=0, pe=False, seed=0):
     x = _rand((rows, C), seed, 2.0) + 0.5
@@ -326,6 +346,10 @@ CHECKS = [
     ("conv3x3 1x148x148 256->128 bf16", lambda: check_conv3x3(1, 148, 148, 256, 128, BF)),
     ("conv tail 1x70x84 128->32->1 bf16", lambda: check_conv_tail(1, 70, 84, 128, BF)),
     ("conv tail 1x56x70 64->32->1 fp16", lambda: check_conv_tail(1, 56, 70, 64, HF)),
+    ("tail fused 2x40x48->70x84 128ch bf16", lambda: check_tail_fused(2, 40, 48, 70, 84, 128, BF)),
+    ("tail fused 1x32x40->56x70 64ch fp16", lambda: check_tail_fused(1, 32, 40, 56, 70, 64, HF)),
+    ("tail fused 1x9x11->14x14 128ch bf16 (one tile)", lambda: check_tail_fused(1, 9, 11, 14, 14, 128, BF)),
+    ("tail fused 3x296x296->518x518 128ch bf16", lambda: check_tail_fused(3, 296, 296, 518, 518, 128, BF)),
     # --- norms ---
     ("layernorm 1370x1024 f32->bf16", lambda: check_layernorm(1370, 1024, BF)),
     ("layernorm 1370x384 f32->fp16 drop cls", lambda: check_layernorm(4 * 137, 384, HF, drop_group=137)),

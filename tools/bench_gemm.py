@@ -63,7 +63,7 @@ def conv(name, n, H, W, ci, co, **kw):
     print(f"{name:34s} M={M:8d} N={co:5d} K={9 * ci:5d}  {ms * 1e3:8.1f} us  {2.0 * M * co * 9 * ci / ms / 1e9:7.1f} TF/s", flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "tail"):
     M = 43840
     if len(sys.argv) > 1 and sys.argv[1] == "prof":     # one launch per shape, for ncu
         def once(fn, iters=1):
@@ -87,3 +87,19 @@ if __name__ == "__main__":
     conv("RCU conv 256->256 @74^2 +res", 32, 74, 74, 256, 256, res=True)
     conv("output_conv1 256->128 @296^2", 32, 296, 296, 256, 128)
     conv("output_conv2 tail 128->32->1 @518^2", 1, 518, 518, 128, 32, tail=True)
+
+
+def tail(n=32, ih=296, iw=296, oh=518, ow=518, c=128):
+    x = torch.randn(n * ih * iw, c, device="cuda").to(DT)
+    w = (torch.randn(32, 9 * c, device="cuda") / (9 * c) ** 0.5).to(DT)
+    b = torch.randn(32, device="cuda")
+    w2 = torch.rand(32, device="cuda")
+    out = torch.zeros(n, oh, ow, device="cuda")
+    ms = timeit(lambda: ops.tail_fused(x, w, b, w2, 0.1, out, n, ih, iw, oh, ow, c))
+    fl = 2.0 * n * oh * ow * 32 * 9 * c
+    print(f"fused tail {n}x{ih}x{iw}->{oh}x{ow} C={c}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TF/s", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "tail":
+    tail()
+    tail(c=64)

@@ -345,12 +345,9 @@ class Engine:
         del p1
         H, W = 14 * hp, 14 * wp
         depth = self._new(BT, H, W, dtype=torch.float32)
-        up = self._new(H * W, self.c_oc1)
-        o1v = o1.view(BT, H8 * W8, self.c_oc1)
-        for f in range(BT):   # per frame: the upsampled 128-channel map (69 MB at 518^2) stays L2-resident
-            ops.bilinear_nhwc(o1v[f], up, 1, H8, W8, H, W, self.c_oc1)                   # :94-96
-            ops.gemm(up, w["oc2.w"], depth[f], bias=w["oc2.b"], epilogue=EPI_TAIL, tail_w=w["oc3.w"],
-                     tail_b=self.oc3_b, conv_shape=(1, H, W, self.c_oc1))                # :97-100 output_conv2
+        # :94-100 bilinear 296->518 + output_conv2 (3x3 -> ReLU -> 1x1 -> ReLU) in one kernel: the upsampled
+        # 128-channel map (2.2 GB per window) is never materialised
+        ops.tail_fused(o1, w["oc2.w"], w["oc2.b"], w["oc3.w"], self.oc3_b, depth, BT, H8, W8, H, W, self.c_oc1)
         return depth
 
     # -------------------------------------------------------------------------------------------

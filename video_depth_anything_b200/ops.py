@@ -181,6 +181,20 @@ def bilinear_nhwc(x: torch.Tensor, out: torch.Tensor, n: int, ih: int, iw: int, 
     return out
 
 
+def tail_fused(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, w2: torch.Tensor, b2: float, out: torch.Tensor,
+               n: int, ih: int, iw: int, oh: int, ow: int, Cc: int):
+    """depth = relu(w2 . relu(conv3x3(bilinear(x -> oh x ow)) + bias) + b2); x h16 NHWC [n,ih,iw,Cc] -> out fp32 [n,oh,ow]."""
+    lib = _lib.load()
+    assert x.is_contiguous() and w.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32
+    assert w.shape == (32, 9 * Cc) and w.dtype == x.dtype
+    if PROFILE is not None:
+        _INFO.update(kind="tail_fused", flops=2.0 * n * oh * ow * 32 * 9 * Cc)
+    check(lib.vda_tail_fused(_p(x), _p(w), _p(bias), _p(w2), float(b2), _p(out), n, ih, iw, oh, ow, Cc,
+                             dt_code(x.dtype), _stream()))
+    _count()
+    return out
+
+
 def bilinear_f32(x: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
     lib = _lib.load()
     n, ih, iw = x.shape
@@ -234,6 +248,6 @@ def _profiled(fn, name):
 
 
 for _n in ("gemm", "layernorm", "groupnorm", "attention_spatial", "attention_temporal", "patch_im2col", "write_cls",
-           "pos_embed_bicubic", "im2col3x3_s2", "bilinear_nhwc", "bilinear_f32", "add_h16", "lsq_scale_shift",
+           "pos_embed_bicubic", "im2col3x3_s2", "bilinear_nhwc", "tail_fused", "bilinear_f32", "add_h16", "lsq_scale_shift",
            "affine_clamp_blend"):
     globals()[_n] = _profiled(globals()[_n], _n)
