@@ -173,22 +173,32 @@ def main():
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     launches0 = ops.LAUNCHES
-    ops.PROFILE = []
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_start.record()
     for i in range(K):
         flush.zero_()                      # evict L2 between steps (256 MB > 126 MB L2)
         ev[i][0].record()
-        d = model.forward(x_dev)
+        d = model.forward(x_dev)           # CUDA-graph replay of the ~330 libvda launches of one window
         ev[i][1].record()
     t_end.record()
     barrier()
-    prof, ops.PROFILE = ops.PROFILE, None
     launches = ops.LAUNCHES - launches0
     clocks = sampler.stop() if sampler else None
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = t_start.elapsed_time(t_end)
+    # per-kernel table: the same K steps once more, launched eagerly with a CUDA-event pair around every libvda
+    # launch (events cannot be recorded per kernel inside a graph replay); shares are relative to these steps
+    ops.PROFILE = []
+    pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(K):
+        flush.zero_()
+        pev[i][0].record()
+        model.forward(x_dev)
+        pev[i][1].record()
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    prof_step_ms = [a.elapsed_time(b) for a, b in pev]
     tmax = torch.tensor([total_ms], device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -218,7 +228,8 @@ def main():
                 "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
                 "peak_kind": f"bf16_tflops_sustained of {pk['src']} (kernel timed inside a long step)",
                 "flops_per_launch": tc_flops / max(tc_n, 1), "avg_launch_ms": tc_ms / max(tc_n, 1),
-                "launches_per_step": tc_n / K, "share_of_step": tc_ms / sum(step_ms), "traffic": None}
+                "launches_per_step": tc_n / K, "share_of_step": tc_ms / sum(prof_step_ms),
+                "measured": "CUDA events around every launch, eager replay of the timed steps", "traffic": None}
     whole = ALGO_TFLOP_PER_WINDOW[args.encoder] * K * B / (sum(step_ms) * 1e-3)
 
     # ---------------- end-to-end arm (host buffers, copies in the timed region) ----------------
@@ -256,6 +267,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{args.encoder} 1x32x518x518 window per GPU per step, random-init weights",
                        "encoder": args.encoder, "frames_per_window": T, "l2": "256 MB flush between steps",
+                       "launch": "CUDA graph replay per window",
                        "parallelism": f"window-sharded replicas x{world}"},
             "tflops_algorithmic": whole if world == 1 else None,
             "frac_of_bf16_sustained": (whole / pk["sustained"]) if world == 1 else None,
@@ -271,7 +283,7 @@ def main():
                                             launches=v["launches"] / K,
                                             tflops=v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0)
                                        for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])],
-                       "step_ms": step_ms}, open(args.profile_out, "w"), indent=1)
+                       "step_ms": step_ms, "eager_profiled_step_ms": prof_step_ms}, open(args.profile_out, "w"), indent=1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -89,6 +89,29 @@ __device__ unsigned long long g_sa_timing[3][8];
 #define SA_TOKEN(x) x
 #endif
 
+// exp2 on the FMA / ALU pipes for a pair of values (Cody-Waite: x = j + f, j = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial, max rel. error 7.7e-5 -- below the 16-bit rounding of P; 2^j by adding j
+// to the exponent field).  A quarter of the exponentials of a score tile take this path so that the MUFU (16 ex2/clk/SM)
+// is no longer the only unit that can produce them.
+#ifndef VDA_SA_POLY_MASK
+#define VDA_SA_POLY_MASK 3     // pair p of a row uses the polynomial when (p & MASK) == MASK; 1: 50%, 3: 25%, 255: none
+                               // (measured per layer: none 0.416 ms, 25% 0.395 ms, 50% 0.445 ms -- issue-slot bound beyond 25%)
+#endif
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));          // 1.5 * 2^23: integer part in the low bits
+  const float2 j = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __fadd2_rn(x, make_float2(-j.x, -j.y));
+  float2 q = __ffma2_rn(make_float2(5.508868381e-02f, 5.508868381e-02f), f, make_float2(2.426040515e-01f, 2.426040515e-01f));
+  q = __ffma2_rn(q, f, make_float2(6.932762417e-01f, 6.932762417e-01f));
+  q = __ffma2_rn(q, f, make_float2(9.999289404e-01f, 9.999289404e-01f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -369,8 +392,10 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
             float2 x0 = __ffma2_rn(make_float2(__uint_as_float(s[c + k]), __uint_as_float(s[c + k + 1])), sc2, nmb2);
             float2 x1 =
                 __ffma2_rn(make_float2(__uint_as_float(s[c + k + 2]), __uint_as_float(s[c + k + 3])), sc2, nmb2);
-            x0.x = exp2f(x0.x); x0.y = exp2f(x0.y);
-            x1.x = exp2f(x1.x); x1.y = exp2f(x1.y);
+            if ((((c + k) >> 1) & VDA_SA_POLY_MASK) == VDA_SA_POLY_MASK) x0 = exp2_poly2(x0);
+            else { x0.x = exp2f(x0.x); x0.y = exp2f(x0.y); }
+            if (((((c + k) >> 1) + 1) & VDA_SA_POLY_MASK) == VDA_SA_POLY_MASK) x1 = exp2_poly2(x1);
+            else { x1.x = exp2f(x1.x); x1.y = exp2f(x1.y); }
             la = __fadd2_rn(la, x0);
             lb = __fadd2_rn(lb, x1);
             pk[k >> 1] = H16<T>::pack2(x0.x, x0.y);
