@@ -127,7 +127,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--encoder", default="vitl", choices=["vitl", "vits"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
-    ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the bounded CPU-baseline sample (~10 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (profiling runs only)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-family time table (JSON) here")
@@ -219,6 +219,7 @@ def main():
         f = fam.setdefault(key, {"ms": 0.0, "flops": 0.0, "launches": 0})
         f["ms"] += s.elapsed_time(e)
         f["flops"] += info.get("flops", 0.0)
+        f["bytes"] = f.get("bytes", 0.0) + info.get("bytes", 0.0)
         f["launches"] += 1
     pk = peaks()
     tc = [v for k, v in fam.items() if k.startswith("gemm") or k.startswith("conv3x3")]
@@ -231,6 +232,21 @@ def main():
                 "launches_per_step": tc_n / K, "share_of_step": tc_ms / sum(prof_step_ms),
                 "measured": "CUDA events around every launch, eager replay of the timed steps", "traffic": None}
     whole = ALGO_TFLOP_PER_WINDOW[args.encoder] * K * B / (sum(step_ms) * 1e-3)
+    # secondary kernels, same measurement: fused attention (tensor work 4*N^2*d per (frame, head); exp-bound, d = 64)
+    # and LayerNorm (HBM-bound: fp32 rows in, 16-bit rows out)
+    others = {}
+    if "attention_spatial" in fam and fam["attention_spatial"]["ms"] > 0:
+        a = fam["attention_spatial"]
+        others["attention_spatial"] = {"bound": "tensor (exp-limited)", "achieved": a["flops"] / (a["ms"] * 1e-3) / 1e12,
+                                       "peak": pk["sustained"], "unit": "TFLOP/s",
+                                       "frac": a["flops"] / (a["ms"] * 1e-3) / 1e12 / pk["sustained"],
+                                       "share_of_step": a["ms"] / sum(prof_step_ms)}
+    if "layernorm" in fam and fam["layernorm"]["ms"] > 0 and fam["layernorm"].get("bytes", 0) > 0:
+        a = fam["layernorm"]
+        gbs = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+        others["layernorm"] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                               "frac": gbs / pk["hbm"], "share_of_step": a["ms"] / sum(prof_step_ms)}
+    roofline["other_kernels"] = others
 
     # ---------------- end-to-end arm (host buffers, copies in the timed region) ----------------
     for _ in range(0 if args.no_e2e else 2):

@@ -99,6 +99,25 @@ def test_full_size_window_vs_oracle(enc, dtype, tol):
     _check(dtype, *fin, f"{enc} 1x32x518x518")
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
+def test_metric_config_518x924_vs_oracle(dtype):
+    """BASELINE.json configs[3] geometry (1280x720 video -> 518x924 network input, 2443 tokens per frame, bicubic
+    pos-embed, non-square maps everywhere) on a short clip, against the fp32 oracle run on the GPU."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    fin, rows, d, ref = stage_report("vitl", 0, (1, 4, 3, 518, 924), 1234, dtype, oracle_device="cuda")
+    assert (ref > 0).float().mean() > 0.99
+    _check(dtype, *fin, "vitl 1x4x518x924")
+
+
+def test_batch_of_clips_equals_single_clips():
+    """BASELINE.json configs[4]: independent clips in one batch give the per-clip results bit-for-bit."""
+    m, _ = build_model("vits", 0, torch.bfloat16)
+    x = torch.randn(2, 8, 3, 56, 70, generator=torch.Generator().manual_seed(11)).cuda()
+    both = m.forward(x)
+    assert torch.equal(both[0], m.forward(x[:1])[0]) and torch.equal(both[1], m.forward(x[1:])[0])
+
+
 def test_sharded_driver_single_process_equals_plain():
     """parallel.infer_video_depth_sharded without a process group is exactly infer_video_depth (N>1 logic is covered
     on CPU with gloo in tests/test_parallel_cpu.py; tests/multi_gpu_check.py runs it under torchrun on N GPUs)."""

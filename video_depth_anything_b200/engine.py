@@ -277,7 +277,8 @@ class Engine:
         qkv = self._new(M, 3 * C)
         o = self._new(M, C)
         for a in (0, 1):                                                                # :165-172
-            ops.layernorm(h, w[f"{p}a{a}.ln.w"], w[f"{p}a{a}.ln.b"], 1e-5, n, pe=w[f"{p}a{a}.pe"], pe_rows_per_frame=hw)
+            ops.layernorm(h, w[f"{p}a{a}.ln.w"], w[f"{p}a{a}.ln.b"], 1e-5, n, pe=w[f"{p}a{a}.pe"], pe_rows_per_frame=hw,
+                          pe_frames=T)                     # rows are (clip, frame, position): frame = (r // hw) % T
             ops.gemm(n, w[f"{p}a{a}.qkv.w"], qkv)
             for b in range(B):
                 s = slice(b * T * hw, (b + 1) * T * hw)

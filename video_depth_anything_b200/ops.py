@@ -96,15 +96,18 @@ def gemm(a: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, bias=None, gam
     return out
 
 
-def layernorm(x: torch.Tensor, w, b, eps: float, out: torch.Tensor, *, drop_group=0, pe=None, pe_rows_per_frame=0):
+def layernorm(x: torch.Tensor, w, b, eps: float, out: torch.Tensor, *, drop_group=0, pe=None, pe_rows_per_frame=0,
+              pe_frames=0):
     """nn.LayerNorm over the last dim; x fp32 or h16 [rows, C] -> out h16."""
     lib = _lib.load()
     Cc = x.shape[-1]
     rows = x.numel() // Cc
     assert x.is_contiguous() and out.is_contiguous()
+    if PROFILE is not None:
+        _INFO.update(kind="layernorm", bytes=float(x.numel() * x.element_size() + out.numel() * out.element_size()))
     check(lib.vda_layernorm(_p(x), int(x.dtype == torch.float32), _p(out), _p(w), _p(b), eps, rows, Cc,
                             dt_code(out.dtype), drop_group, _p(pe), pe_rows_per_frame,
-                            0 if pe is None else pe.shape[0], _stream()))
+                            0 if pe is None else (pe_frames or pe.shape[0]), _stream()))
     _count()
     return out
 
