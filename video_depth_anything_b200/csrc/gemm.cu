@@ -31,7 +31,7 @@ constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 2;
 struct GemmDev {
   int M, N, K;
   int block_n, num_k_blocks, tiles_m, tiles_n, num_tiles, stages;
-  uint32_t stage_bytes, tmem_cols, acc_stride;
+  uint32_t stage_bytes, tx_bytes, tmem_cols, acc_stride;   // tx_bytes: TMA bytes per stage issued by one CTA
   // conv addressing
   int H, W, bw, bh, tiles_x, tiles_y, cblocks;
   // epilogue
@@ -52,6 +52,7 @@ struct GemmDev {
   const float* tail_w;
   float tail_b;
   int staged;   // LINEAR: transpose the tile through shared memory (fp32 residual / fp32 output streams)
+  int pair;     // host only: launch the cta_group::2 variant
 };
 
 // 4 consecutive columns as two packed fp32 pairs (FFMA2 / FADD2 / FMUL2 process a pair per instruction)
@@ -125,7 +126,12 @@ __device__ __forceinline__ F4 lds128(uint32_t addr) {
 constexpr uint32_t kStageTile = 32 * 32 * 4;            // per-warp epilogue staging tile (bytes)
 constexpr uint32_t kStagingBytes = kEpiWarps * kStageTile;
 
-template <typename T, int EPI, bool CONV, bool STAGED, int SPEC>
+// CTA2: cta_group::2 -- the two CTAs of a cluster (one TPC) work on a 256-row tile pair with ONE stream of
+// M = 256 UMMAs issued by the leader (rank 0).  Each CTA loads its own 128 rows of A and only HALF of the B tile
+// (block_n/2 rows), so the L2 -> smem operand traffic and the smem writes per SM drop by a third and the smem
+// reads of the tensor core from 96 to 64 B/clk/SM; accumulator rows 128r..128r+127 live in CTA r's TMEM and are
+// drained by that CTA's own epilogue warps.
+template <typename T, int EPI, bool CONV, bool STAGED, int SPEC, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
@@ -150,24 +156,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 32 * kEpiWarps);
+      mbar_init(&tempty_bar[s], (CTA2 ? 2 : 1) * 32 * kEpiWarps);   // pair: the leader collects both epilogues
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, p.tmem_cols);
+  if (warp == 1) {
+    if (CTA2) tmem_alloc2(&tmem_base_s, p.tmem_cols);
+    else tmem_alloc(&tmem_base_s, p.tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;
+  // persistent tile loop: a CTA pair shares tile index, CTA r takes m block 2*pair + r
+  const int tile0 = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     // warp-uniform control flow, one elected lane issues (see elect_one)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
       const int n_blk = tile % p.tiles_n;
-      const int m_blk = tile / p.tiles_n;
+      const int m_blk = CTA2 ? 2 * (tile / p.tiles_n) + rank : tile / p.tiles_n;
       int img = 0, x0 = 0, y0 = 0;
       if (CONV) {
         const int per_img = p.tiles_x * p.tiles_y;
@@ -180,16 +193,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int kb = 0; kb < p.num_k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[stage], p.stage_bytes);
           uint8_t* sA = smem_gen + static_cast<size_t>(stage) * p.stage_bytes;
           uint8_t* sB = sA + kABytes;
-          if (CONV) {
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            tma_load_4d(sA, &tmA, &full_bar[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
+          if (CTA2) {
+            // both CTAs load (A rows of their own m block, their half of the B rows); all bytes are credited to the
+            // leader's full barrier, which expects the sum
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * p.tx_bytes);
+            if (CONV) {
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              tma_load_4d_pair(sA, &tmA, &full_bar[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
+            } else {
+              tma_load_2d_pair(sA, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            }
+            tma_load_2d_pair(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * p.block_n + rank * (p.block_n >> 1));
           } else {
-            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes);
+            if (CONV) {
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              tma_load_4d(sA, &tmA, &full_bar[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
+            } else {
+              tma_load_2d(sA, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            }
+            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * p.block_n);
           }
-          tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * p.block_n);
         }
         __syncwarp();
         if (CONV && ++cb == p.cblocks) { cb = 0; ++tap; }
@@ -198,12 +224,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    const uint32_t idesc = umma_idesc(H16<T>::kUmmaFmt, static_cast<uint32_t>(p.block_n));
+    const uint32_t idesc = umma_idesc_m(H16<T>::kUmmaFmt, static_cast<uint32_t>(p.block_n), CTA2 ? 256u : 128u);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < p.num_tiles && rank == 0; tile += tile_step) {   // pair: only the leader issues
       mbar_wait(&tempty_bar[as], aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * p.acc_stride;
@@ -217,10 +243,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // +32 bytes (16 elements) along K inside the 128-byte swizzle atom = +2 in the address field
-            umma_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CTA2) umma_f16_pair(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (kb == p.num_k_blocks - 1) umma_commit(&tfull_bar[as]);   // accumulator ready for the epilogue
+          if (CTA2) {
+            umma_commit_pair(&empty_bar[stage]);                                // frees the slot in both CTAs
+            if (kb == p.num_k_blocks - 1) umma_commit_pair(&tfull_bar[as]);     // both epilogues may drain
+          } else {
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+            if (kb == p.num_k_blocks - 1) umma_commit(&tfull_bar[as]);   // accumulator ready for the epilogue
+          }
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -239,9 +271,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int rsub = lane >> 3;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
       const int n_blk = tile % p.tiles_n;
-      const int m_blk = tile / p.tiles_n;
+      const int m_blk = CTA2 ? 2 * (tile / p.tiles_n) + rank : tile / p.tiles_n;
       const int col_base = n_blk * p.block_n;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
 
@@ -255,7 +287,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int rem = m_blk - img * per_img;
           const int y = (rem / p.tiles_x) * p.bh + r / p.bw;
           const int x = (rem % p.tiles_x) * p.bw + r % p.bw;
-          valid = (y < p.H) && (x < p.W);
+          valid = (y < p.H) && (x < p.W) && (m_blk < p.tiles_m);
           out_row = (static_cast<long long>(img) * p.H + y) * p.W + x;
         } else {
           out_row = static_cast<long long>(m_blk) * BLOCK_M + r;
@@ -284,7 +316,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int rem = m_blk - img * per_img;
             const int y = (rem / p.tiles_x) * p.bh + r / p.bw;
             const int x = (rem % p.tiles_x) * p.bw + r % p.bw;
-            o = ((y < p.H) && (x < p.W)) ? (img * p.H + y) * p.W + x : -1;
+            o = ((y < p.H) && (x < p.W) && (m_blk < p.tiles_m)) ? (img * p.H + y) * p.W + x : -1;
             rr = o;
           } else {
             const int m = m_blk * BLOCK_M + r;
@@ -308,13 +340,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (EPI == VDA_EPI_LINEAR && (p.res1 || p.res2)) {
           // pull the residual rows of this CTA's NEXT tile towards L2 now: its epilogue then reads them at L2
           // latency instead of queueing behind HBM (the epilogue is a dependent load -> math -> store chain)
-          const int nxt = tile + gridDim.x;
+          const int nxt = tile + tile_step;
           if (nxt < p.num_tiles) {
-            const int n_blk2 = nxt % p.tiles_n, m_blk_save = m_blk;
-            (void)m_blk_save;
+            const int n_blk2 = nxt % p.tiles_n;
             int o2, r2i;
             {
-              const int m_blk2 = nxt / p.tiles_n;
+              const int m_blk2 = CTA2 ? 2 * (nxt / p.tiles_n) + rank : nxt / p.tiles_n;
               const int r = q * 32 + lane;
               if (CONV) {
                 const int per_img = p.tiles_x * p.tiles_y;
@@ -322,7 +353,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int rem = m_blk2 - img * per_img;
                 const int y = (rem / p.tiles_x) * p.bh + r / p.bw;
                 const int x = (rem % p.tiles_x) * p.bw + r % p.bw;
-                o2 = ((y < p.H) && (x < p.W)) ? (img * p.H + y) * p.W + x : -1;
+                o2 = ((y < p.H) && (x < p.W) && (m_blk2 < p.tiles_m)) ? (img * p.H + y) * p.W + x : -1;
                 r2i = o2;
               } else {
                 const int m = m_blk2 * BLOCK_M + r;
@@ -593,17 +624,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      if (CTA2) mbar_arrive_leader(&tempty_bar[as]);   // the leader's issuer waits for both CTAs' epilogues
+      else mbar_arrive(&tempty_bar[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (CTA2) tmem_dealloc2(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -666,18 +699,42 @@ static int pick_block_n(int N, int tiles_m) {
   return bn;
 }
 
-template <typename T, int EPI, bool CONV, bool STAGED, int SPEC = 0>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, size_t smem, cudaStream_t st) {
-  auto kfn = gemm_kernel<T, EPI, CONV, STAGED, SPEC>;
+template <typename T, int EPI, bool CONV, bool STAGED, int SPEC, bool CTA2>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, size_t smem, cudaStream_t st) {
+  auto kfn = gemm_kernel<T, EPI, CONV, STAGED, SPEC, CTA2>;
   static size_t attr_smem = 0;   // per instantiation: largest dynamic smem opted in so far
   if (smem > attr_smem) {
     VDA_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_smem = smem;
   }
-  const int grid = d.num_tiles < sm_count() ? d.num_tiles : sm_count();
-  kfn<<<grid, kThreads, smem, st>>>(tmA, tmB, d);
+  if (!CTA2) {
+    const int grid = d.num_tiles < sm_count() ? d.num_tiles : sm_count();
+    kfn<<<grid, kThreads, smem, st>>>(tmA, tmB, d);
+  } else {
+    // CTA pairs: clusters of 2 (same TPC), one tile pair per cluster and round
+    int pairs = sm_count() / 2;
+    if (d.num_tiles < pairs) pairs = d.num_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VDA_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, d));
+  }
   VDA_CUDA(cudaGetLastError());
   return 0;
+}
+template <typename T, int EPI, bool CONV, bool STAGED, int SPEC = 0>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, size_t smem, cudaStream_t st) {
+  if (d.pair) return launch2<T, EPI, CONV, STAGED, SPEC, true>(tmA, tmB, d, smem, st);
+  return launch2<T, EPI, CONV, STAGED, SPEC, false>(tmA, tmB, d, smem, st);
 }
 
 template <typename T>
@@ -784,13 +841,25 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
   }
   d.tiles_n = (p->N + d.block_n - 1) / d.block_n;
   d.num_tiles = d.tiles_m * d.tiles_n;
+  // CTA pairs (cta_group::2, M = 256): when there are enough 256-row tile pairs to fill the 74 TPCs; each CTA then
+  // loads only block_n/2 rows of B per stage
+  // (not for K <= 256: those GEMMs are bound by their output stream, measured slower in pair mode)
+  d.pair = (p->epilogue != VDA_EPI_TAIL && d.block_n % 32 == 0 && d.tiles_m >= 2 && d.num_k_blocks >= 8 &&
+            ((d.tiles_m + 1) / 2) * d.tiles_n >= sm_count() / 2) ? 1 : 0;
+  {
+    static const char* force = getenv("VDA_GEMM_PAIR");    // debug hook (tools/bench_gemm.py)
+    if (force && force[0] == '0') d.pair = 0;
+  }
+  if (d.pair) d.num_tiles = ((d.tiles_m + 1) / 2) * d.tiles_n;
+  const uint32_t b_rows = d.pair ? d.block_n / 2 : d.block_n;   // B rows loaded (and stored) per CTA and stage
   {
     cuuint64_t dims[2] = {(cuuint64_t)p->K, (cuuint64_t)p->N};
     cuuint64_t strides[1] = {(cuuint64_t)p->K * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)d.block_n};
+    cuuint32_t box[2] = {64, (cuuint32_t)b_rows};
     if (make_tensor_map(&tmB, p->dtype, p->Wt, 2, dims, strides, box)) return 1;
   }
-  d.stage_bytes = kABytes + static_cast<uint32_t>(d.block_n) * BLOCK_K * 2;
+  d.tx_bytes = kABytes + b_rows * BLOCK_K * 2;
+  d.stage_bytes = d.tx_bytes;
   // block_n*128 is a multiple of 2048 only when block_n % 16 == 0 -> every stage stays 1024-byte aligned
   d.stage_bytes = (d.stage_bytes + 1023u) & ~1023u;
   // 227 KB per CTA: 1 KB alignment slack + static barriers, the epilogue staging tiles, the rest for the operand ring
