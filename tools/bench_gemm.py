@@ -63,7 +63,7 @@ def conv(name, n, H, W, ci, co, **kw):
     print(f"{name:34s} M={M:8d} N={co:5d} K={9 * ci:5d}  {ms * 1e3:8.1f} us  {2.0 * M * co * 9 * ci / ms / 1e9:7.1f} TF/s", flush=True)
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "tail"):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("tail", "ln")):
     M = 43840
     if len(sys.argv) > 1 and sys.argv[1] == "prof":     # one launch per shape, for ncu
         def once(fn, iters=1):
@@ -103,3 +103,17 @@ def tail(n=32, ih=296, iw=296, oh=518, ow=518, c=128):
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "tail":
     tail()
     tail(c=64)
+
+
+def ln_bench(rows=43840, C=1024):
+    x = torch.randn(rows, C, device="cuda")
+    w = torch.randn(C, device="cuda"); b = torch.randn(C, device="cuda")
+    out = torch.empty(rows, C, device="cuda", dtype=DT)
+    ms = timeit(lambda: ops.layernorm(x, w, b, 1e-6, out))
+    gb = rows * C * 6 / 1e9
+    ref = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-6)
+    print(f"layernorm {rows}x{C} f32->bf16: {ms * 1e3:7.1f} us  {gb / ms * 1e3:6.0f} GB/s  max err {(out.float() - ref).abs().max().item():.3e}", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ln":
+    ln_bench()

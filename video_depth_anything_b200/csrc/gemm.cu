@@ -156,7 +156,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], (CTA2 ? 2 : 1) * 32 * kEpiWarps);   // pair: the leader collects both epilogues
+      mbar_init(&tempty_bar[s], (CTA2 ? 2 : 1) * kEpiWarps);   // one arrival per epilogue warp; pair: both CTAs
     }
     mbar_fence_init();
   }
@@ -623,9 +623,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      // one arrival per warp (a cluster-scope release per thread costs a fence each): every lane has waited for its
+      // own tcgen05.ld, the warp converges, lane 0 signals the (leader's) issuer
       tc_fence_before();
-      if (CTA2) mbar_arrive_leader(&tempty_bar[as]);   // the leader's issuer waits for both CTAs' epilogues
-      else mbar_arrive(&tempty_bar[as]);
+      __syncwarp();
+      if (lane == 0) {
+        if (CTA2 && rank != 0) mbar_arrive_leader(&tempty_bar[as]);
+        else mbar_arrive(&tempty_bar[as]);
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
