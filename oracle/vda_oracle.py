@@ -377,6 +377,57 @@ def preprocess_frame(frame_u8: np.ndarray, input_size: int) -> np.ndarray:
     return np.ascontiguousarray(np.transpose(img, (2, 0, 1))).astype(np.float32)
 
 
+def _cubic_coeffs_f32(x: np.ndarray) -> np.ndarray:
+    """OpenCV's interpolateCubic (A = -0.75) evaluated in float32, as cv2.resize does for CV_32F images."""
+    f = np.float32
+    A, x = f(-0.75), x.astype(np.float32)
+    c0 = ((A * (x + f(1)) - f(5) * A) * (x + f(1)) + f(8) * A) * (x + f(1)) - f(4) * A
+    c1 = ((A + f(2)) * x - (A + f(3))) * x * x + f(1)
+    c2 = ((A + f(2)) * (f(1) - x) - (A + f(3))) * (f(1) - x) * (f(1) - x) + f(1)
+    c3 = f(1) - c0 - c1 - c2
+    return np.stack([c0, c1, c2, c3], -1).astype(np.float32)
+
+
+def resize_cubic_opencv(img: np.ndarray, nw: int, nh: int) -> np.ndarray:
+    """cv2.resize(img float32 [H,W,C], (nw, nh), INTER_CUBIC) restated from OpenCV's published generic algorithm
+    (third-party dependency of util/transform.py:109-111; opencv-python 4.13 in this image): source coordinate
+    (d + 0.5) * (1 / (dst/src)) - 0.5 rounded to float32, taps floor-1..floor+2 with replicated borders, horizontal
+    pass then vertical pass, float32 throughout; same-size = identity.  Pinned in tests/test_oracle_golden.py
+    against cv2 with IPP switched off (<= 1 float32 ulp of 1.0); cv2's default IPP build of the same resize differs
+    from this generic path by up to ~1e-4 (implementation-defined, the tolerance the device kernel is held to
+    against stock cv2)."""
+    H, W = img.shape[:2]
+    if (H, W) == (nh, nw):
+        return img.astype(np.float32).copy()
+
+    def axis(n, src):
+        scale = 1.0 / (n / src)
+        f = ((np.arange(n) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        c = _cubic_coeffs_f32(f - s.astype(np.float32))
+        return np.clip(s[:, None] + np.arange(-1, 3)[None], 0, src - 1), c
+
+    ix, cx = axis(nw, W)
+    iy, cy = axis(nh, H)
+    img = img.astype(np.float32)
+    rows = np.zeros((H, nw, img.shape[2]), np.float32)
+    for k in range(4):
+        rows = rows + img[:, ix[:, k], :] * cx[None, :, k, None]
+    out = np.zeros((nh, nw, img.shape[2]), np.float32)
+    for k in range(4):
+        out = out + rows[iy[:, k]] * cy[:, k, None, None]
+    return out
+
+
+def preprocess_frame_generic(frame_u8: np.ndarray, input_size: int) -> np.ndarray:
+    """preprocess_frame with the resize done by resize_cubic_opencv (no cv2 call)."""
+    h0, w0 = frame_u8.shape[:2]
+    nh, nw = get_resize_hw(h0, w0, input_size)
+    img = resize_cubic_opencv(frame_u8.astype(np.float32) / 255.0, nw, nh)
+    img = (img - [0.485, 0.456, 0.406]) / [0.229, 0.224, 0.225]
+    return np.ascontiguousarray(np.transpose(img, (2, 0, 1))).astype(np.float32)
+
+
 @torch.no_grad()
 def infer_video_depth(sd, frames: np.ndarray, encoder: str, input_size: int = 518,
                       mode: str = "affine", forward_fn=None):

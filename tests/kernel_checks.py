@@ -182,6 +182,26 @@ def check_tail_fused(n, ih, iw, oh, ow, ci, dt, seed=0):
     return _err(out, ref), _tol(ref, dt) * 4
 
 
+def check_preprocess(n, h0, w0, input_size, seed=0):
+    """device preprocessing (uint8 -> /255 -> INTER_CUBIC resize -> normalise -> CHW) vs the oracle's restatement of
+    OpenCV's generic algorithm (float rounding only) and vs stock cv2 as the reference calls it (util/transform.py;
+    the IPP build of cv2 differs from OpenCV's own generic path by ~1e-4 of the [0,1] pixel range, i.e. ~4e-4 after
+    the division by std)."""
+    import numpy as np
+    from oracle import vda_oracle as O
+    rng = np.random.default_rng(seed)
+    frames = rng.integers(0, 256, (n, h0, w0, 3), dtype=np.uint8)
+    sel = [n - 1, 0, n // 2]
+    ref = torch.from_numpy(np.stack([O.preprocess_frame_generic(frames[i], input_size) for i in sel]))
+    stock = torch.from_numpy(np.stack([O.preprocess_frame(frames[i], input_size) for i in sel]))
+    nh, nw = ref.shape[2:]
+    out = ops.preprocess_frames(torch.from_numpy(frames).to(DEV), torch.tensor(sel, dtype=torch.int32, device=DEV), nh, nw)
+    torch.cuda.synchronize()
+    e_stock = _err(out, stock.to(DEV))
+    assert e_stock < 1e-3, f"vs stock cv2: {e_stock}"
+    return _err(out, ref.to(DEV)), 5e-6
+
+
 # ------------------------------------------------------------------------------------------------ others
 def check_layernorm(rows, C, dt, in_f32=True, drop_group=0, pe=False, seed=0):
     x = _rand((rows, C), seed, 2.0) + 0.5
@@ -350,6 +370,10 @@ CHECKS = [
     ("tail fused 1x32x40->56x70 64ch fp16", lambda: check_tail_fused(1, 32, 40, 56, 70, 64, HF)),
     ("tail fused 1x9x11->14x14 128ch bf16 (one tile)", lambda: check_tail_fused(1, 9, 11, 14, 14, 128, BF)),
     ("tail fused 3x296x296->518x518 128ch bf16", lambda: check_tail_fused(3, 296, 296, 518, 518, 128, BF)),
+    ("preprocess 60x80 -> 98x126 (upscale)", lambda: check_preprocess(5, 60, 80, 98)),
+    ("preprocess 720x1280 -> 518x924 (downscale)", lambda: check_preprocess(3, 720, 1280, 518)),
+    ("preprocess 518x518 identity", lambda: check_preprocess(3, 518, 518, 518)),
+    ("preprocess 300x1000 (aspect guard)", lambda: check_preprocess(3, 300, 1000, 518)),
     # --- norms ---
     ("layernorm 1370x1024 f32->bf16", lambda: check_layernorm(1370, 1024, BF)),
     ("layernorm 1370x384 f32->fp16 drop cls", lambda: check_layernorm(4 * 137, 384, HF, drop_group=137)),

@@ -141,6 +141,20 @@ def attention_temporal(qkv: torch.Tensor, out: torch.Tensor, T: int, hw: int, Cc
     return out
 
 
+def preprocess_frames(frames_u8: torch.Tensor, idx: torch.Tensor, nh: int, nw: int) -> torch.Tensor:
+    """uint8 RGB [N,H0,W0,3] (device) + int32 frame indices [n] (device) -> normalised fp32 [n,3,nh,nw]
+    (util/transform.py Resize(INTER_CUBIC) / NormalizeImage / PrepareForNet)."""
+    lib = _lib.load()
+    assert frames_u8.is_contiguous() and frames_u8.dtype == torch.uint8 and frames_u8.dim() == 4 and frames_u8.shape[3] == 3
+    assert idx.dtype == torch.int32 and idx.is_contiguous()
+    n = idx.numel()
+    out = torch.empty(n, 3, nh, nw, dtype=torch.float32, device=frames_u8.device)
+    check(lib.vda_preprocess_frames(_p(frames_u8), _p(idx), _p(out), n, frames_u8.shape[1], frames_u8.shape[2], nh, nw,
+                                    _stream()))
+    _count()
+    return out
+
+
 def patch_im2col(x: torch.Tensor, out: torch.Tensor):
     """x fp32 [frames,3,H,W] -> out h16 [frames*hp*wp, kpad]"""
     lib = _lib.load()
@@ -250,7 +264,7 @@ def _profiled(fn, name):
     return wrapper
 
 
-for _n in ("gemm", "layernorm", "groupnorm", "attention_spatial", "attention_temporal", "patch_im2col", "write_cls",
+for _n in ("preprocess_frames", "gemm", "layernorm", "groupnorm", "attention_spatial", "attention_temporal", "patch_im2col", "write_cls",
            "pos_embed_bicubic", "im2col3x3_s2", "bilinear_nhwc", "tail_fused", "bilinear_f32", "add_h16", "lsq_scale_shift",
            "affine_clamp_blend"):
     globals()[_n] = _profiled(globals()[_n], _n)

@@ -3,9 +3,10 @@ metric_depth/video_depth_anything/video_depth.py:35-154): same constructor kwarg
 `forward` / `infer_video_depth` signatures and error behaviour, with every operator executed by libvda's
 sm_100a kernels.  There is no CPU path: calling `forward` without the CUDA extension or off-GPU raises.
 
-The long-video driver keeps the reference's host preprocessing (util/transform.py, cv2 INTER_CUBIC) but does
-everything after the H2D copy on the device: per-window forward, output resize, key-frame least-squares
-alignment, clamp and 8-frame cross-fade, one D2H copy per window of finished frames.
+The long-video driver does everything after the upload of the uint8 frames on the device: window gather + cv2-style
+INTER_CUBIC resize + normalisation (util/transform.py), per-window forward, output resize, key-frame least-squares
+alignment, clamp and 8-frame cross-fade; frames stream in and finished depths stream out through pinned staging
+buffers while the windows compute.
 """
 from __future__ import annotations
 
@@ -19,8 +20,7 @@ import torch.nn as nn
 from . import ops
 from .engine import Engine
 from .synth import ENCODER_DIMS, synth_state_dict
-from .windows import (INFER_LEN, INTERP_LEN, KEYFRAMES, OVERLAP, get_resize_hw, preprocess_frames,
-                      window_source_indices)
+from .windows import INFER_LEN, INTERP_LEN, KEYFRAMES, OVERLAP, get_resize_hw, window_source_indices
 
 
 class VideoDepthAnything(nn.Module):
@@ -99,12 +99,18 @@ class VideoDepthAnything(nn.Module):
                           window_ids: Optional[Sequence[int]] = None, raw_only=False):
         """frames uint8 [N,H0,W0,3] -> (float32 [N,H0,W0], target_fps)   (video_depth.py:166-254).
 
+        Everything after the upload of the uint8 frames runs on the device: per-window gather + cv2-style
+        INTER_CUBIC resize + normalisation (one kernel), forward (CUDA-graph replay), output resize, key-frame
+        least squares, clamp and cross-fade.  Frames are uploaded in chunks through pinned staging buffers while
+        earlier windows compute, finished depth frames stream back the same way; the host never touches a pixel.
         `fp32` is accepted for signature compatibility; operand precision is the engine's dtype (bf16/fp16
         tensor-core operands, fp32 accumulation / residual / statistics).
         `window_ids` / `raw_only` are the multi-GPU hooks (parallel.py): compute only those windows and return
         the raw, resized per-window depths [len(window_ids),32,H0,W0] on the device, skipping alignment."""
         if torch.device(device).type != "cuda":
             raise RuntimeError("infer_video_depth: the B200 engine has no CPU path (device must be 'cuda')")
+        if frames.ndim != 4 or frames.shape[3] != 3 or frames.dtype != np.uint8:
+            raise ValueError("frames must be uint8 [N,H0,W0,3]")
         self.to(device)
         eng = self._ensure_engine()
         n = frames.shape[0]
@@ -112,33 +118,80 @@ class VideoDepthAnything(nn.Module):
         nh, nw = get_resize_hw(h0, w0, input_size)
         wins = window_source_indices(n)
         ids = list(range(len(wins))) if window_ids is None else list(window_ids)
-        needed = sorted({i for k in ids for i in wins[k]})
         with torch.cuda.device(self._device):
-            pre = preprocess_frames(frames, needed, input_size)          # host, each source frame once
-            slot = {i: j for j, i in enumerate(needed)}
-            pre_dev = torch.from_numpy(pre).pin_memory().to(self._device, non_blocking=True)
+            if not ids:
+                return torch.empty(0, INFER_LEN, h0, w0, device=self._device) if raw_only else \
+                    (np.empty((0, h0, w0), np.float32), target_fps)
+            needed = sorted({i for k in ids for i in wins[k]})
+            up = FrameUploader(frames, needed, self._device)
             raws = []
             aligner = None if raw_only else WindowAligner(n, h0, w0, self._device,
                                                           "identity" if self.metric else "affine")
             for k in ids:
-                idx = torch.tensor([slot[i] for i in wins[k]], device=self._device)
-                x = pre_dev.index_select(0, idx).unsqueeze(0)            # [1,32,3,nh,nw]
-                d = eng.forward(x)[0]                                    # [32,nh,nw] fp32
+                up.ensure(max(wins[k]))                                      # H2D of the chunks this window needs
+                idx = torch.tensor([up.slot[i] for i in wins[k]], dtype=torch.int32, device=self._device)
+                x = ops.preprocess_frames(up.dev, idx, nh, nw).unsqueeze(0)  # [1,32,3,nh,nw]   (:197-201)
+                d = eng.forward(x)[0]                                        # [32,nh,nw] fp32   (:203-205)
                 if (nh, nw) != (h0, w0):
-                    d = ops.bilinear_f32(d, h0, w0)                      # video_depth.py:208
+                    d = ops.bilinear_f32(d, h0, w0)                          # video_depth.py:208
                 if raw_only:
                     raws.append(d)
                 else:
                     aligner.push(d)
             if raw_only:
-                return torch.stack(raws) if raws else torch.empty(0, INFER_LEN, h0, w0, device=self._device)
+                return torch.stack(raws)
             return aligner.result(), target_fps
+
+
+class FrameUploader:
+    """Chunked, asynchronous H2D of the uint8 frames a rank needs (pinned double buffer, copy stream); windows wait
+    only for the chunks that hold their frames, so the upload overlaps the compute of earlier windows."""
+
+    CHUNK = 64
+
+    def __init__(self, frames: np.ndarray, needed: List[int], device):
+        self.frames, self.needed, self.device = frames, needed, device
+        self.slot = {i: j for j, i in enumerate(needed)}
+        h0, w0 = frames.shape[1:3]
+        self.dev = torch.empty(len(needed), h0, w0, 3, dtype=torch.uint8, device=device)
+        self.stage = [torch.empty(self.CHUNK, h0, w0, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.stage_free = [None, None]           # event: staging buffer consumed by its H2D copy
+        self.stream = torch.cuda.Stream(device=device)
+        self.uploaded = 0                        # number of `needed` entries issued so far
+        self.chunk_no = 0
+
+    def ensure(self, max_frame: int) -> None:
+        """Issue uploads until source frame `max_frame` is covered, then make the current stream wait for them."""
+        target = self.slot[max_frame] + 1
+        last_ev = None
+        while self.uploaded < target:
+            lo, hi = self.uploaded, min(self.uploaded + self.CHUNK, len(self.needed))
+            b = self.chunk_no & 1
+            if self.stage_free[b] is not None:
+                self.stage_free[b].synchronize()
+            src_idx = self.needed[lo:hi]
+            st = self.stage[b][:hi - lo]
+            if src_idx[-1] - src_idx[0] == hi - lo - 1:                      # contiguous run: plain slice copy
+                np.copyto(st.numpy(), self.frames[src_idx[0]:src_idx[-1] + 1])
+            else:
+                np.take(self.frames, src_idx, axis=0, out=st.numpy())
+            with torch.cuda.stream(self.stream):
+                self.dev[lo:hi].copy_(st, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            self.stage_free[b] = ev
+            last_ev = ev
+            self.uploaded = hi
+            self.chunk_no += 1
+        if last_ev is not None:
+            torch.cuda.current_stream().wait_event(last_ev)
 
 
 class WindowAligner:
     """Sequential scale/shift alignment + cross-fade of consecutive windows on the device
-    (video_depth.py:216-252, utils/util.py:40-74).  Finished frames are copied to pinned host memory
-    asynchronously; (scale, shift) never leave the GPU."""
+    (video_depth.py:216-252, utils/util.py:40-74).  (scale, shift) never leave the GPU; frames that can no longer
+    change (everything but the last 8) are streamed to the host through pinned staging buffers while the next
+    windows compute."""
 
     def __init__(self, n_frames: int, h0: int, w0: int, device, mode: str = "affine"):
         self.n, self.h0, self.w0, self.device, self.mode = n_frames, h0, w0, device, mode
@@ -152,7 +205,37 @@ class WindowAligner:
         step = 1.0 / (INTERP_LEN - 1)
         self.blend_w = torch.tensor([0.0] + [i * step for i in range(1, INTERP_LEN - 1)] + [1.0],
                                     dtype=torch.float32, device=device)
-        self.scales = []
+        self.host = np.empty((n_frames, h0, w0), dtype=np.float32)
+        self.stage = [torch.empty(INFER_LEN, h0, w0, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.pending = [None, None]          # (event, lo, hi) of the D2H copy sitting in each staging buffer
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.sent = 0                        # frames already handed to the D2H pipeline
+        self.batch_no = 0
+
+    def _drain(self, b: int) -> None:
+        if self.pending[b] is not None:
+            ev, lo, hi = self.pending[b]
+            ev.synchronize()
+            np.copyto(self.host[lo:hi], self.stage[b][:hi - lo].numpy())
+            self.pending[b] = None
+
+    def _send(self, upto: int) -> None:
+        """Stream frames [sent, upto) (final values) to the host."""
+        upto = min(upto, self.n)
+        while self.sent < upto:
+            lo, hi = self.sent, min(self.sent + INFER_LEN, upto)
+            b = self.batch_no & 1
+            self._drain(b)
+            ready = torch.cuda.Event()
+            ready.record()                                   # the frames are final once the current stream gets here
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(ready)
+                self.stage[b][:hi - lo].copy_(self.out[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            self.pending[b] = (ev, lo, hi)
+            self.sent = hi
+            self.batch_no += 1
 
     def push(self, d: torch.Tensor) -> None:
         """d: raw depths of the next window, fp32 [32,h0,w0]."""
@@ -162,19 +245,20 @@ class WindowAligner:
             self.out[:INFER_LEN].copy_(d)                                 # window 0 copied unclamped (:222-225)
             self.ref = torch.stack([d[KEYFRAMES[0]], d[KEYFRAMES[1]]])
             self.filled = INFER_LEN
-            return
-        if self.mode == "affine":
-            ops.lsq_scale_shift(d[:align_len], self.ref, self.ss, self.scratch)      # :227-232
-        tail = self.out[self.filled - INTERP_LEN:self.filled]
-        ops.affine_clamp_blend(d[align_len:OVERLAP], self.ss, tail, prev=tail, blend_w=self.blend_w)   # :234-239
-        new = self.out[self.filled:self.filled + INFER_LEN - OVERLAP]
-        ops.affine_clamp_blend(d[OVERLAP:], self.ss, new)                                              # :241-244
-        ref1 = self.ref[1:2]
-        ops.affine_clamp_blend(d[KEYFRAMES[1]:KEYFRAMES[1] + 1], self.ss, ref1)                       # :246-250
-        self.filled += INFER_LEN - OVERLAP
+        else:
+            if self.mode == "affine":
+                ops.lsq_scale_shift(d[:align_len], self.ref, self.ss, self.scratch)      # :227-232
+            tail = self.out[self.filled - INTERP_LEN:self.filled]
+            ops.affine_clamp_blend(d[align_len:OVERLAP], self.ss, tail, prev=tail, blend_w=self.blend_w)   # :234-239
+            new = self.out[self.filled:self.filled + INFER_LEN - OVERLAP]
+            ops.affine_clamp_blend(d[OVERLAP:], self.ss, new)                                              # :241-244
+            ref1 = self.ref[1:2]
+            ops.affine_clamp_blend(d[KEYFRAMES[1]:KEYFRAMES[1] + 1], self.ss, ref1)                       # :246-250
+            self.filled += INFER_LEN - OVERLAP
+        self._send(self.filled - INTERP_LEN)          # the last 8 frames are still cross-faded with the next window
 
     def result(self) -> np.ndarray:
-        host = torch.empty(self.n, self.h0, self.w0, dtype=torch.float32).pin_memory()
-        host.copy_(self.out[:self.n], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return host.numpy()
+        self._send(self.n)
+        self._drain(0)
+        self._drain(1)
+        return self.host
