@@ -130,6 +130,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the bounded CPU-baseline sample (~10 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (profiling runs only)")
+    ap.add_argument("--video-frames", type=int, default=2048, help="length of the long-video arm (0 = skip)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-family time table (JSON) here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -270,6 +271,35 @@ def main():
                                     "h2d_bytes_per_step": x_host.numel() * 4,
                                     "d2h_bytes_per_step": out_host.numel() * 4}
 
+    # ---------------- long-video arm (BASELINE.json configs[2]): infer_video_depth from host frames to host depths ---
+    video = None
+    if args.video_frames > 0:
+        import numpy as np
+        from video_depth_anything_b200.parallel import infer_video_depth_sharded
+        from video_depth_anything_b200.windows import num_windows
+        base = np.random.default_rng(0).integers(0, 256, (64, H, Wd, 3), dtype=np.uint8)
+        frames = base[np.arange(args.video_frames) % 64]
+        infer_video_depth_sharded(model, frames[:66 * world], 24, device=dev)      # warm-up: graphs for 32/22-frame encodes
+        barrier()
+        l0 = ops.LAUNCHES
+        t0 = time.perf_counter()
+        depths, _ = infer_video_depth_sharded(model, frames, 24, device=dev)
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        tv = torch.tensor([dt_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        nwin = num_windows(args.video_frames)
+        if rank == 0:
+            assert depths.shape == (args.video_frames, H, Wd) and np.isfinite(depths[::97]).all()
+            video = {"workload": f"{args.encoder} {args.video_frames}x518x518 uint8 video, 32-frame windows, overlap 10, "
+                                 f"host frames -> host depths (upload, device preprocessing, feature reuse, alignment, "
+                                 f"download all inside the timed region)",
+                     "video_frames_per_s": args.video_frames / tv.item(), "windows": nwin,
+                     "window_slots_per_s": nwin * 32 / tv.item(), "seconds": tv.item(),
+                     "gpu_launches_rank0": ops.LAUNCHES - l0, "timing": "host wall clock, max over ranks"}
+        del frames, depths
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -287,7 +317,8 @@ def main():
                        "parallelism": f"window-sharded replicas x{world}"},
             "tflops_algorithmic": whole if world == 1 else None,
             "frac_of_bf16_sustained": (whole / pk["sustained"]) if world == 1 else None,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "video": video, "gpu_launches": launches,
+            "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
         if args.profile_out:

@@ -18,7 +18,7 @@ timeout -k 5 900 python bench.py --steps 5 --warmup 3 --profile-out gpurun_out/p
 echo "bench rc=$?" >> gpurun_out/bench_vitl.log
 tail -n 5 gpurun_out/bench_vitl.log
 if [ "${NCU:-0}" = "1" ]; then
-  CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
+  CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --video-frames 0"
   N=$(python -c "import json;print(json.loads(open('gpurun_out/bench_vitl.log').readline())['gpu_launches']//5)" 2>/dev/null || echo 340)
   $CMD > gpurun_out/ncu_plain.log 2>&1 &&
   timeout -k 5 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * N)) -c $N --csv \

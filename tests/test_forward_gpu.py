@@ -130,3 +130,30 @@ def test_sharded_driver_single_process_equals_plain():
     a, _ = m.infer_video_depth(g["frames"], 24, input_size=c["input_size"], device="cuda")
     b, _ = infer_video_depth_sharded(m, g["frames"], 24, input_size=c["input_size"])
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,h0,w0,size", [(70, 56, 70, 56), (33, 60, 80, 98), (5, 42, 42, 42)],
+                         ids=["70f-same-size", "33f-resized", "5f-padded"])
+def test_feature_reuse_is_bit_identical(n, h0, w0, size):
+    """encoding each source frame once and reusing its tap features across overlapping windows
+    gives exactly the frames of the plain per-window path (kernels are batch-invariant), on multi-window videos,
+    resized inputs and a video shorter than one window (padded with its last frame)."""
+    m, _ = build_model("vits", 0, torch.bfloat16)
+    frames = np.random.default_rng(n).integers(0, 256, (n, h0, w0, 3), dtype=np.uint8)
+    a, _ = m.infer_video_depth(frames, 24, input_size=size, device="cuda", reuse_features=True)
+    b, _ = m.infer_video_depth(frames, 24, input_size=size, device="cuda", reuse_features=False)
+    assert a.shape == (n, h0, w0) and np.isfinite(a).all()
+    assert np.array_equal(a, b)
+
+
+def test_infer_video_depth_vs_oracle_resized_multiwindow():
+    """Device preprocessing (INTER_CUBIC resize + normalise), feature reuse, output resize and alignment together
+    against the oracle's infer_video_depth (cv2 preprocessing, per-window forward) on a 2-window resized video."""
+    from video_depth_anything_b200.synth import MODEL_CONFIGS, synth_state_dict
+    m, _ = build_model("vits", 0, torch.float16)
+    sd = synth_state_dict(**MODEL_CONFIGS["vits"], seed=0)
+    frames = np.random.default_rng(5).integers(0, 256, (40, 45, 64, 3), dtype=np.uint8)
+    out, _ = m.infer_video_depth(frames, 24, input_size=56, device="cuda")
+    ref = O.infer_video_depth(sd, frames, "vits", input_size=56)
+    mx, p999, mean = O.rel_err(torch.from_numpy(out), torch.from_numpy(ref))
+    assert mx <= TOL, f"rel err max {mx:.3e} p99.9 {p999:.3e} mean {mean:.3e}"

@@ -69,9 +69,36 @@ preprocess_kernel(const uint8_t* __restrict__ frames, const int* __restrict__ id
   }
 }
 
+// Gather / scatter of whole per-frame slabs (encoder-feature cache of the long-video driver): frame i of the copy goes
+// from src slab src_idx[i] to dst slab dst_idx[i] (a null index list = identity).  One 16-byte vector per thread.
+__global__ void __launch_bounds__(256)
+copy_frames_kernel(const uint4* __restrict__ src, const int* __restrict__ src_idx, uint4* __restrict__ dst,
+                   const int* __restrict__ dst_idx, long long vec_per_frame) {
+  const int f = blockIdx.y;
+  const uint4* s = src + static_cast<long long>(src_idx ? src_idx[f] : f) * vec_per_frame;
+  uint4* d = dst + static_cast<long long>(dst_idx ? dst_idx[f] : f) * vec_per_frame;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < vec_per_frame;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    d[i] = s[i];
+}
+
 }  // namespace vda
 
 using namespace vda;
+
+extern "C" int vda_copy_frames(const void* src, const int32_t* src_idx, void* dst, const int32_t* dst_idx, int n,
+                               int64_t frame_bytes, void* stream) {
+  VDA_CHECK(n > 0 && frame_bytes > 0 && frame_bytes % 16 == 0, "copy_frames: frame size must be a positive multiple of 16 B");
+  VDA_CHECK((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % 16 == 0, "copy_frames: unaligned pointer");
+  const long long vec = frame_bytes / 16;
+  long long gx = (vec + 256 * 4 - 1) / (256 * 4);
+  if (gx < 1) gx = 1;
+  if (gx > 148 * 8) gx = 148 * 8;
+  copy_frames_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(src), src_idx, static_cast<uint4*>(dst), dst_idx, vec);
+  VDA_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int vda_preprocess_frames(const uint8_t* frames, const int32_t* idx, float* out, int n, int H0, int W0, int nh,
                                      int nw, void* stream) {

@@ -155,6 +155,20 @@ def preprocess_frames(frames_u8: torch.Tensor, idx: torch.Tensor, nh: int, nw: i
     return out
 
 
+def copy_frames(src: torch.Tensor, src_idx: Optional[torch.Tensor], dst: torch.Tensor, dst_idx: Optional[torch.Tensor],
+                n: int) -> torch.Tensor:
+    """dst[dst_idx[i]] = src[src_idx[i]] for i < n over the leading (frame) axis; idx: device int32 or None (identity)."""
+    lib = _lib.load()
+    assert src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype
+    fb = src[0].numel() * src.element_size()
+    assert fb == dst[0].numel() * dst.element_size()
+    for ix in (src_idx, dst_idx):
+        assert ix is None or (ix.dtype == torch.int32 and ix.is_contiguous() and ix.numel() >= n)
+    check(lib.vda_copy_frames(_p(src), _p(src_idx), _p(dst), _p(dst_idx), n, fb, _stream()))
+    _count()
+    return dst
+
+
 def patch_im2col(x: torch.Tensor, out: torch.Tensor):
     """x fp32 [frames,3,H,W] -> out h16 [frames*hp*wp, kpad]"""
     lib = _lib.load()
@@ -264,7 +278,7 @@ def _profiled(fn, name):
     return wrapper
 
 
-for _n in ("preprocess_frames", "gemm", "layernorm", "groupnorm", "attention_spatial", "attention_temporal", "patch_im2col", "write_cls",
+for _n in ("preprocess_frames", "copy_frames", "gemm", "layernorm", "groupnorm", "attention_spatial", "attention_temporal", "patch_im2col", "write_cls",
            "pos_embed_bicubic", "im2col3x3_s2", "bilinear_nhwc", "tail_fused", "bilinear_f32", "add_h16", "lsq_scale_shift",
            "affine_clamp_blend"):
     globals()[_n] = _profiled(globals()[_n], _n)
