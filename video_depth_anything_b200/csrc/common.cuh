@@ -273,7 +273,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(smem_u32(bar))
       : "memory");
 }

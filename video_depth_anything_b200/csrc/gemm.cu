@@ -506,6 +506,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (ok && orow[it] >= 0) rnxt[it] = load4f(rbase[it] + col);
           };
           if (has_res && c_begin < c_end) load_res(c_begin);
+          // bias / LayerScale segments are fetched one chunk ahead as well (the first before the accumulator is
+          // ready): loaded at their point of use, the L2 round trip sat in front of every chunk's math
+          F4 bias_nxt = {}, gamma_nxt = {};
+          auto load_bg = [&](int c0) {
+            const int col = col_base + c0 + 4 * cg;
+            if (col < p.N && (c0 + 32 <= c_end || cg < 4)) {
+              if (has_bias) bias_nxt = load4f(p.bias + col);
+              if (has_gamma) gamma_nxt = load4f(p.gamma + col);
+            }
+          };
+          if (c_begin < c_end) load_bg(c_begin);
           mbar_wait(&tfull_bar[as], aphase);
           tc_fence_after();
           for (int c0 = c_begin; c0 < c_end; c0 += 32) {
@@ -535,13 +546,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               // are interleaved by the scheduler (the GELU chain alone is ~100 cycles deep)
 #pragma unroll
               for (int it = 0; it < 8; ++it) v[it] = lds128(stg + stg_off(it * 4 + rsub, cg));
+              const F4 bias4 = bias_nxt, gamma4 = gamma_nxt;
+              if (c0 + 32 < c_end) load_bg(c0 + 32);
               if (has_bias) {
-                const F4 bias4 = load4f(p.bias + col);
 #pragma unroll
                 for (int it = 0; it < 8; ++it) v[it] = add4(v[it], bias4);
               }
               if (has_gamma) {
-                const F4 gamma4 = load4f(p.gamma + col);
 #pragma unroll
                 for (int it = 0; it < 8; ++it) v[it] = mul4(v[it], gamma4);
               }

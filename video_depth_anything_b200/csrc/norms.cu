@@ -16,8 +16,10 @@ layernorm_kernel(const void* __restrict__ in, T* __restrict__ out, const float* 
                  const float* __restrict__ b, float eps, long long rows, int C, int drop_group,
                  const float* __restrict__ pe, int pe_rows_per_frame, int pe_frames) {
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  // rows are visited last-to-first: the producer (a GEMM epilogue walking the row tiles upwards) wrote the highest
+  // rows last, so they are still in the 126 MB L2, and the consumer GEMM starts at row 0, which this kernel writes last
+  const long long row = rows - 1 - (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (row < 0) return;
   long long orow = row;
   if (drop_group > 0) {
     if (row % drop_group == 0) return;          // cls token: not consumed by the head (use_clstoken=False)
