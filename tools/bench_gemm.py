@@ -74,6 +74,7 @@ if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("tail",
         plain("proj (+ls, fp32 residual in place)", M, 1024, 1024, out_f32=True, res_f32=True)
         plain("fc1 + GELU", M, 4096, 1024, act=ACT_GELU)
         plain("fc2 (+ls, fp32 residual in place)", M, 1024, 4096, out_f32=True, res_f32=True)
+        plain("qkv", M, 3072, 1024)
         sys.exit(0)
     plain("qkv", M, 3072, 1024)
     plain("proj (+ls, fp32 residual in place)", M, 1024, 1024, out_f32=True, res_f32=True)

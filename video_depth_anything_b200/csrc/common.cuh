@@ -87,21 +87,20 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// erf-GELU x Phi(x) for a pair, evaluated as x * sigmoid(2u(x)) with 2u(x) = 2 atanh(erf(x / sqrt 2)) = x q(x^2), q an
+// even polynomial of degree 8 fitted on |x| <= 7.5 (beyond that the sigmoid is saturated and any growing q is exact to
+// fp32): max abs error 3.7e-6, max relative error 2e-5 (a 16-bit output ulp is >= 4.9e-4 relative).  The constants
+// carry the factor -log2(e), so Phi = 1 / (1 + 2^t): 8 packed FMA-pipe operations + 4 MUFU per element pair,
+// versus 15 + 4 for the Abramowitz-Stegun erf used before (the fc1 epilogue is instruction-bound).
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
-  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
-  const float2 d = __ffma2_rn(ax, make_float2(0.23164190f, 0.23164190f), make_float2(1.f, 1.f));   // 1 + p |x| / sqrt2
-  const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
-  float2 q = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
-  q = __ffma2_rn(q, t, make_float2(1.421413741f, 1.421413741f));
-  q = __ffma2_rn(q, t, make_float2(-0.284496736f, -0.284496736f));
-  q = __ffma2_rn(q, t, make_float2(0.254829592f, 0.254829592f));
-  q = __fmul2_rn(q, t);
-  const float2 w = __fmul2_rn(__fmul2_rn(ax, make_float2(-0.72134752f, -0.72134752f)), ax);   // -(x^2 / 2) log2 e
-  const float2 e = make_float2(exp2f(w.x), exp2f(w.y));
-  const float2 erf_abs = __ffma2_rn(make_float2(-q.x, -q.y), e, make_float2(1.f, 1.f));
-  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-  const float2 hax = make_float2(fabsf(hx.x), fabsf(hx.y));
-  return __ffma2_rn(hax, erf_abs, hx);
+  const float2 x2 = __fmul2_rn(x, x);
+  float2 q = __ffma2_rn(make_float2(-3.291989515e-06f, -3.291989515e-06f), x2, make_float2(8.931364573e-05f, 8.931364573e-05f));
+  q = __ffma2_rn(q, x2, make_float2(3.548166424e-04f, 3.548166424e-04f));
+  q = __ffma2_rn(q, x2, make_float2(-1.052177921e-01f, -1.052177921e-01f));
+  q = __ffma2_rn(q, x2, make_float2(-2.302048445e+00f, -2.302048445e+00f));
+  const float2 t = __fmul2_rn(q, x);
+  const float2 d = __fadd2_rn(make_float2(exp2f(t.x), exp2f(t.y)), make_float2(1.f, 1.f));
+  return __fmul2_rn(x, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));

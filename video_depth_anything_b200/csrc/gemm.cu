@@ -482,6 +482,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const bool has_res = SPEC != 0 ? SPEC == 3 : (p.res1 != nullptr && p.res1_f32);
           const bool out_f32 = SPEC != 0 ? SPEC == 3 : p.out_f32 != 0;
           const bool relu_copy = SPEC != 0 ? false : p.out_relu != nullptr;
+          const bool has_r1h = SPEC != 0 ? false : (p.res1 != nullptr && !p.res1_f32);   // 16-bit residuals (RCU skips)
+          const bool has_r2h = SPEC != 0 ? false : p.res2 != nullptr;
           const int nch = p.block_n >> 4;                                  // 16-column units in the tile
           const int c_begin = (eh ? (nch + 1) / 2 : 0) * 16;
           const int c_end = (eh ? nch : (nch + 1) / 2) * 16;
@@ -495,6 +497,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             obase[it] = reinterpret_cast<char*>(p.out) + static_cast<long long>(orow[it]) * p.ldo * (out_f32 ? 4 : 2);
             all_rows = all_rows && orow[it] >= 0;
           }
+          all_rows = __all_sync(0xffffffffu, all_rows);   // warp-uniform: the common full-tile case stores without row tests
           // residual row segments are loaded one chunk ahead (the first one before the accumulator is ready), so
           // their HBM/L2 latency hides behind the TMEM drain and the math of the previous chunk
           F4 rnxt[8];
@@ -505,7 +508,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int it = 0; it < 8; ++it)
               if (ok && orow[it] >= 0) rnxt[it] = load4f(rbase[it] + col);
           };
+          // 16-bit residual row segments (4 columns = 8 bytes per lane and row), same one-chunk-ahead scheme
+          uint2 r1h[8], r2h[8];
+          auto load_resh = [&](int c0) {
+            const int col = col_base + c0 + 4 * cg;
+            const bool ok = col < p.N && (c0 + 32 <= c_end || cg < 4);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              if (ok && orow[it] >= 0) {
+                if (has_r1h)
+                  r1h[it] = *reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(p.res1) +
+                                                            static_cast<long long>(rrow[it]) * p.ldr1 + col);
+                if (has_r2h)
+                  r2h[it] = *reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(p.res2) +
+                                                            static_cast<long long>(orow[it]) * p.ldo + col);
+              }
+            }
+          };
           if (has_res && c_begin < c_end) load_res(c_begin);
+          if ((has_r1h || has_r2h) && c_begin < c_end) load_resh(c_begin);
           // bias / LayerScale segments are fetched one chunk ahead as well (the first before the accumulator is
           // ready): loaded at their point of use, the L2 round trip sat in front of every chunk's math
           F4 bias_nxt = {}, gamma_nxt = {};
@@ -567,17 +588,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int it = 0; it < 8; ++it) v[it] = add4(v[it], rnxt[it]);
               }
+              if (has_r1h) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  F4 r;
+                  r.a = H16<T>::unpack2(r1h[it].x); r.b = H16<T>::unpack2(r1h[it].y);
+                  v[it] = add4(v[it], r);
+                }
+              }
+              if (has_r2h) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  F4 r;
+                  r.a = H16<T>::unpack2(r2h[it].x); r.b = H16<T>::unpack2(r2h[it].y);
+                  v[it] = add4(v[it], r);
+                }
+              }
             }
             if (has_res && c0 + 32 < c_end) load_res(c0 + 32);   // next chunk's residual, consumed one iteration later
+            if ((has_r1h || has_r2h) && c0 + 32 < c_end) load_resh(c0 + 32);
             if (col_ok) {
               const int cbyte = col * (out_f32 ? 4 : 2);
-#pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                if (!all_rows && orow[it] < 0) continue;
+              auto store_row = [&](int it) {
                 if (out_f32) store4f(reinterpret_cast<float*>(obase[it] + cbyte), v[it]);
                 else store4h<T>(reinterpret_cast<T*>(obase[it] + cbyte), v[it]);
                 if (relu_copy)
                   store4h<T>(reinterpret_cast<T*>(p.out_relu) + static_cast<long long>(orow[it]) * p.ldo + col, relu4(v[it]));
+              };
+              if (all_rows) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) store_row(it);
+              } else {
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                  if (orow[it] >= 0) store_row(it);
               }
             }
             __syncwarp();
@@ -879,11 +923,10 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
   // block_n*128 is a multiple of 2048 only when block_n % 16 == 0 -> every stage stays 1024-byte aligned
   d.stage_bytes = (d.stage_bytes + 1023u) & ~1023u;
   // 227 KB per CTA: 1 KB alignment slack + static barriers, the epilogue staging tiles, the rest for the operand ring
-  // LINEAR epilogue variant (measured with tools/bench_gemm.py): the shared-memory transpose wins whenever the
-  // global traffic of the epilogue is stores only or fp32 (coalesced rows); with 16-bit residual operands the
-  // row-per-thread path (128-bit loads, no extra smem traffic next to the operand ring) is faster.
-  d.staged = (p->epilogue == VDA_EPI_GEGLU ||
-              (p->epilogue == VDA_EPI_LINEAR && !((p->res1 && !p->res1_f32) || p->res2))) ? 1 : 0;
+  // LINEAR epilogue variant (measured with tools/bench_gemm.py): the shared-memory transpose (coalesced row segments
+  // for every residual load and store) wins for all LINEAR epilogues, 16-bit residuals included (RCU conv @148^2:
+  // 703 -> 627 us); the row-per-thread path remains for CONVT and as a debug variant.
+  d.staged = (p->epilogue == VDA_EPI_GEGLU || p->epilogue == VDA_EPI_LINEAR) ? 1 : 0;
   if (p->epilogue == VDA_EPI_LINEAR) {   // debug hook (tools/bench_gemm.py): force the epilogue variant
     static const char* force = getenv("VDA_GEMM_STAGED");
     if (force && (force[0] == '0' || force[0] == '1')) d.staged = force[0] - '0';
