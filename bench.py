@@ -34,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGO_TFLOP_PER_WINDOW = {"vitl": 44.950, "vits": 3.881}     # SURVEY.md §6 / BASELINE.md §2 (32x518x518)
+BASELINE_A100_FP16_FPS = {"vitl": 1000.0 / 14.0, "vits": 1000.0 / 7.5}   # BASELINE.md §1 (reference README.md:49-64)
 
 
 def peaks():
@@ -232,6 +233,21 @@ def main():
                 "flops_per_launch": tc_flops / max(tc_n, 1), "avg_launch_ms": tc_ms / max(tc_n, 1),
                 "launches_per_step": tc_n / K, "share_of_step": tc_ms / sum(prof_step_ms),
                 "measured": "CUDA events around every launch, eager replay of the timed steps", "traffic": None}
+    # DRAM traffic per launch from the committed `ncu --set full` capture of the four hot encoder GEMMs (proj, fc1,
+    # fc2, qkv at M=43840: 96 of the family's launches per window), next to their algorithmic operand bytes
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if args.encoder == "vitl" and os.path.exists(tpath):
+        t = json.load(open(tpath))
+        algo = {"proj": 43840 * 1024 * 2 + 1024 * 1024 * 2 + 2 * 43840 * 1024 * 4,
+                "fc1": 43840 * 1024 * 2 + 4096 * 1024 * 2 + 43840 * 4096 * 2,
+                "fc2": 43840 * 4096 * 2 + 4096 * 1024 * 2 + 2 * 43840 * 1024 * 4,
+                "qkv": 43840 * 1024 * 2 + 3072 * 1024 * 2 + 43840 * 3072 * 2}
+        det = {n: {"dram_bytes": t[f"gemm_prof.ncu-rep:{i}"]["dram_bytes"], "algorithmic_bytes": algo[n]}
+               for i, n in enumerate(("proj", "fc1", "fc2", "qkv")) if f"gemm_prof.ncu-rep:{i}" in t}
+        if len(det) == 4:
+            roofline["traffic"] = sum(v["dram_bytes"] for v in det.values()) / 4
+            roofline["traffic_unit"] = "bytes per launch, mean of the 4 hot encoder GEMM shapes (ncu dram__bytes_read+write)"
+            roofline["traffic_detail"] = det
     whole = ALGO_TFLOP_PER_WINDOW[args.encoder] * K * B / (sum(step_ms) * 1e-3)
     # secondary kernels, same measurement: fused attention (tensor work 4*N^2*d per (frame, head); exp-bound, d = 64)
     # and LayerNorm (HBM-bound: fp32 rows in, 16-bit rows out)
@@ -310,7 +326,11 @@ def main():
         line = {
             "metric": "frames/s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "p50_window_latency_ms": statistics.median(step_ms),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (value / world / BASELINE_A100_FP16_FPS[args.encoder]) if world == 1 else None,
+            "baseline": "BASELINE.md: reference README latency on 1x A100 fp16 (vitl 14 ms/frame = 71.4 frames/s, vits "
+                        "7.5 ms = 133 frames/s), other hardware; 1 GPU only",
+            "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{args.encoder} 1x32x518x518 window per GPU per step, random-init weights",
                        "encoder": args.encoder, "frames_per_window": T, "l2": "256 MB flush between steps",
                        "launch": "CUDA graph replay per window",

@@ -83,10 +83,15 @@ __device__ unsigned long long g_sa_timing[3][8];
 #define SA_T(i) do { } while (0)
 #endif
 
-#ifdef VDA_SA_NO_TOKEN
-#define SA_TOKEN(x) do { } while (0)
-#else
+// Exp-phase hand-over token between the two softmax warpgroups (-DVDA_SA_TOKEN): off by default.  Micro-benchmarks
+// (tools/microbench/exp_phase.cu, mufu_issue.cu) show that a lone warp per scheduler issues one MUFU.EX2 per ~9.7
+// cycles (1315 cycles per 128x128 tile for the kernel's instruction mix) while two warps per scheduler share the
+// dispatch port and need ~2000 cycles for two tiles whatever the MUFU / polynomial split, so exclusive ownership of
+// the MUFU buys nothing any more; letting the warpgroups drift freely measured 0.385 vs 0.396 ms per layer.
+#ifdef VDA_SA_TOKEN
 #define SA_TOKEN(x) x
+#else
+#define SA_TOKEN(x) do { } while (0)
 #endif
 
 // exp2 on the FMA / ALU pipes for a pair of values (Cody-Waite: x = j + f, j = round(x), f in [-0.5, 0.5];
@@ -284,6 +289,7 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
     // turns: a token (named barriers 1 / 2) is handed over after each exp phase, and a warpgroup runs everything
     // else of its step (S load, row max, TMEM stores, barriers) while the other one owns the MUFU.
     const int tok_mine = 1 + t, tok_other = 2 - t;
+    (void)tok_mine; (void)tok_other;
     if (t == 1) SA_TOKEN(named_bar_arrive(tok_other, 256));     // warpgroup A owns the first exp phase
 
     for (int i = 0; i < n_my; ++i) {
