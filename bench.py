@@ -9,8 +9,9 @@ their own windows with no data-path collective and the aggregate is reported as 
 
 Printed JSON (rank 0, one line):
   value        model frames/s, inputs resident in HBM, timed with CUDA events, max over ranks
-  e2e          same metric through the public API with HOST buffers: pinned H2D of the window + forward + D2H of
-               the depth map inside the timed region
+  e2e          same metric through the public API with HOST buffers: every step's pinned H2D of its window, forward
+               and D2H of its depth map inside the timed region (double-buffered by the caller, host wall clock)
+  video        BASELINE.json configs[2]: infer_video_depth on a 2048-frame uint8 video, host frames -> host depths
   roofline     dominant kernel family = the tcgen05 GEMM/implicit-conv kernel; achieved = algorithmic FLOPs of
                those launches / their CUDA-event time, measured in the timed region; peak = MEASURED_PEAKS.json
   cpu_baseline the oracle port (oracle/vda_oracle.py, torch fp32 on the host cores) on a bounded sample
@@ -266,26 +267,62 @@ def main():
     roofline["other_kernels"] = others
 
     # ---------------- end-to-end arm (host buffers, copies in the timed region) ----------------
-    for _ in range(0 if args.no_e2e else 2):
-        model.forward(x_host.to(dev, non_blocking=True))
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    t0 = time.perf_counter()
-    for i in range(0 if args.no_e2e else K):
-        xd = x_host.to(dev, non_blocking=True)
-        dd = model.forward(xd)
-        out_host.copy_(dd, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller consumes the depth map each step
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    tm = torch.tensor([e2e_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    e2e = None if args.no_e2e else {"value": frames_total / (tm.item() * 1e-3), "unit": "frames/s",
-                                    "h2d_bytes_per_step": x_host.numel() * 4,
-                                    "d2h_bytes_per_step": out_host.numel() * 4}
+    # Every step uploads its own window from pinned host memory, runs VideoDepthAnything.forward and reads the depth map
+    # back to pinned host memory.  The caller double-buffers: the upload of step i+1 and the download of step i run on
+    # copy streams next to the forward of step i+1 / i (a serving loop's normal shape); the host consumes each result
+    # one step later, and all K uploads, forwards and downloads lie inside the timed region.
+    e2e = None
+    if not args.no_e2e:
+        up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream()
+        xbuf = [torch.empty_like(x_dev) for _ in range(2)]
+        out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+
+        def e2e_loop(n):
+            ev_up = [torch.cuda.Event(), torch.cuda.Event()]
+            ev_free = [None, None]                     # forward that last read xbuf[b] has finished
+            ev_down = [None, None]
+            with torch.cuda.stream(up):
+                xbuf[0].copy_(x_host, non_blocking=True)
+                ev_up[0].record(up)
+            for i in range(n):
+                b = i & 1
+                main.wait_event(ev_up[b])
+                dd = model.forward(xbuf[b])
+                done = torch.cuda.Event()
+                done.record(main)
+                ev_free[b] = done
+                if i + 1 < n:                          # upload of the next window overlaps this forward
+                    with torch.cuda.stream(up):
+                        if ev_free[1 - b] is not None:
+                            up.wait_event(ev_free[1 - b])
+                        xbuf[1 - b].copy_(x_host, non_blocking=True)
+                        ev_up[1 - b].record(up)
+                if ev_down[b] is not None:
+                    ev_down[b].synchronize()           # the caller consumes result i-2 before its buffer is reused
+                with torch.cuda.stream(down):
+                    down.wait_event(done)
+                    out_hosts[b].copy_(dd, non_blocking=True)
+                    dd.record_stream(down)
+                    ev_down[b] = torch.cuda.Event()
+                    ev_down[b].record(down)
+            for e in ev_down:
+                if e is not None:
+                    e.synchronize()
+
+        e2e_loop(2)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(K)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        tm = torch.tensor([e2e_ms], device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e = {"value": frames_total / (tm.item() * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
+               "pipeline": "double-buffered: H2D of step i+1 and D2H of step i overlap the forward; host wall clock"}
 
     # ---------------- long-video arm (BASELINE.json configs[2]): infer_video_depth from host frames to host depths ---
     video = None

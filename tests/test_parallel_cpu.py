@@ -78,3 +78,38 @@ def test_gather_world2_matches_single_process(tmp_path, n_frames):
     a = O.align_windows([w[i].copy() for w in got for i in range(INFER_LEN)], n_frames, "affine")
     b = O.align_windows([w[i].copy() for w in ref for i in range(INFER_LEN)], n_frames, "affine")
     assert np.array_equal(a, b) and a.shape[0] == n_frames
+
+
+def _stream_worker(rank, world, port, n_frames, out_path):
+    from video_depth_anything_b200.parallel import stream_window_depths
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        parts = partition_windows(num_windows(n_frames), world)
+        counts = [len(p) for p in parts]
+        mine = [fake_raw(k) for k in parts[rank]]
+        local = torch.stack(mine) if mine else torch.empty(0, INFER_LEN, 6, 5)
+        got = [local] if rank == 0 else []
+        order = []
+        for r, stack in stream_window_depths(local if rank else None, counts, (6, 5), torch.float32, "cpu", dst=0):
+            order.append(r)
+            got.append(stack.clone())
+        if rank == 0:
+            assert order == [r for r in range(1, world) if counts[r] > 0]
+            np.save(out_path, torch.cat(got).numpy())
+        else:
+            assert got == []
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_frames", [(2, 70), (3, 131), (3, 23)])
+def test_stream_collect_matches_single_process(tmp_path, world, n_frames):
+    """The point-to-point streaming collection (rank 0 keeps its own block, the others send) yields every other
+    rank's window stack in window order; (3, 23) has ranks with no windows at all."""
+    port = _free_port()
+    out = str(tmp_path / "streamed.npy")
+    mp.spawn(_stream_worker, args=(world, port, n_frames, out), nprocs=world, join=True)
+    got = np.load(out)
+    ref = torch.stack([fake_raw(i) for i in range(num_windows(n_frames))]).numpy()
+    assert got.shape == ref.shape and np.array_equal(got, ref)

@@ -226,11 +226,13 @@ def tail_fused(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, w2: torch.T
     return out
 
 
-def bilinear_f32(x: torch.Tensor, oh: int, ow: int) -> torch.Tensor:
+def bilinear_f32(x: torch.Tensor, oh: int, ow: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     n, ih, iw = x.shape
     assert x.is_contiguous() and x.dtype == torch.float32
-    out = torch.empty(n, oh, ow, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(n, oh, ow, dtype=torch.float32, device=x.device)
+    assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (n, oh, ow)
     check(lib.vda_bilinear_f32(_p(x), _p(out), n, ih, iw, oh, ow, _stream()))
     _count()
     return out

@@ -12,6 +12,8 @@ that is how tests/test_parallel_cpu.py covers the N>1 logic without GPUs.
 """
 from __future__ import annotations
 
+import os
+import time
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -65,6 +67,31 @@ def gather_window_depths(local: torch.Tensor, counts: Sequence[int], dst: int = 
     return torch.cat([bufs[r][:counts[r]] for r in range(world)], dim=0)
 
 
+def stream_window_depths(local: Optional[torch.Tensor], counts: Sequence[int], shape_hw, dtype, device, dst: int = 0,
+                         group=None):
+    """Point-to-point variant of the gather for the streaming driver: every rank other than `dst` sends its raw
+    window stack `[counts[rank], 32, H, W]` to `dst` (NCCL send over NVLink); on `dst` this is a generator that
+    posts all receives up front and yields `(rank, stack)` in rank order (= window order), so the caller aligns
+    rank r's windows while rank r+1's are still in flight.  `dst`'s own windows are not part of the stream."""
+    rank, world = _world(group)
+    if world == 1:
+        return
+    if rank != dst:
+        if counts[rank] > 0:
+            assert local is not None and local.shape[0] == counts[rank]
+            dist.send(local.contiguous(), dst=dst, group=group)
+        return
+    h, w = shape_hw
+    bufs, works = {}, {}
+    for r in range(world):
+        if r != dst and counts[r] > 0:
+            bufs[r] = torch.empty(counts[r], INFER_LEN, h, w, dtype=dtype, device=device)
+            works[r] = dist.irecv(bufs[r], src=r, group=group)
+    for r in sorted(bufs):
+        works[r].wait()
+        yield r, bufs[r]
+
+
 @torch.no_grad()
 def infer_video_depth_sharded(model, frames: np.ndarray, target_fps, input_size: int = 518, device=None,
                               dst: int = 0, group=None):
@@ -79,9 +106,50 @@ def infer_video_depth_sharded(model, frames: np.ndarray, target_fps, input_size:
         return model.infer_video_depth(frames, target_fps, input_size=input_size, device=device)
     n, h0, w0 = frames.shape[:3]
     parts = partition_windows(num_windows(n), world)
+    counts = [len(p) for p in parts]
+    if dst == 0:
+        # streaming form: rank 0 owns the first block of windows, so it aligns them (and streams the finished frames
+        # to the host) while it computes; the other ranks' stacks arrive point-to-point and are aligned in rank order
+        if rank != 0:
+            t0 = time.perf_counter()
+            raw = model.infer_video_depth(frames, target_fps, input_size=input_size, device=device,
+                                          window_ids=list(parts[rank]), raw_only=True)
+            if os.environ.get("VDA_TRACE_VIDEO") == "1":
+                t1 = time.perf_counter()
+                torch.cuda.synchronize(raw.device)
+                print(f"video trace rank {rank}: enqueued +{(t1 - t0) * 1e3:.0f} ms, computed "
+                      f"+{(time.perf_counter() - t0) * 1e3:.0f} ms", flush=True)
+            for _ in stream_window_depths(raw, counts, (h0, w0), torch.float32, raw.device, dst=0, group=group):
+                pass
+            return None, target_fps
+        dev = torch.device(device)
+        trace = os.environ.get("VDA_TRACE_VIDEO") == "1"       # debug: synchronising wall-clock stamps of the phases
+        stamps = [("start", time.perf_counter())]
+
+        def stamp(name):
+            if trace:
+                torch.cuda.synchronize(dev)
+                stamps.append((name, time.perf_counter()))
+
+        with torch.cuda.device(dev):
+            aligner = WindowAligner(n, h0, w0, dev, "identity" if model.metric else "affine")
+            stamp("aligner allocated")
+            model.infer_video_depth(frames, target_fps, input_size=input_size, device=dev, window_ids=list(parts[0]),
+                                    aligner=aligner)
+            stamp("own windows computed + aligned")
+            for r, stack in stream_window_depths(None, counts, (h0, w0), torch.float32, dev, dst=0, group=group):
+                stamp(f"received rank {r}")
+                for k in range(stack.shape[0]):
+                    aligner.push(stack[k])
+                stamp(f"aligned rank {r}")
+            out = aligner.result()
+            stamp("drained to host")
+            if trace:
+                print("video trace: " + ", ".join(f"{a} +{(t - stamps[0][1]) * 1e3:.0f} ms" for a, t in stamps[1:]), flush=True)
+            return out, target_fps
     raw = model.infer_video_depth(frames, target_fps, input_size=input_size, device=device,
                                   window_ids=list(parts[rank]), raw_only=True)         # [k_r,32,h0,w0] on device
-    allraw = gather_window_depths(raw, [len(p) for p in parts], dst=dst, group=group)
+    allraw = gather_window_depths(raw, counts, dst=dst, group=group)
     if rank != dst:
         return None, target_fps
     with torch.cuda.device(allraw.device):
@@ -91,4 +159,4 @@ def infer_video_depth_sharded(model, frames: np.ndarray, target_fps, input_size:
         return aligner.result(), target_fps
 
 
-__all__ = ["partition_windows", "gather_window_depths", "infer_video_depth_sharded", "INFER_LEN"]
+__all__ = ["partition_windows", "gather_window_depths", "stream_window_depths", "infer_video_depth_sharded", "INFER_LEN"]

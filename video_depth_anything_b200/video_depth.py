@@ -10,7 +10,10 @@ buffers while the windows compute.
 """
 from __future__ import annotations
 
+import queue
+import threading
 from collections import OrderedDict
+from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -96,7 +99,8 @@ class VideoDepthAnything(nn.Module):
     # ---- long-video driver -------------------------------------------------------------------
     @torch.no_grad()
     def infer_video_depth(self, frames: np.ndarray, target_fps, input_size=518, device="cuda", fp32=False,
-                          window_ids: Optional[Sequence[int]] = None, raw_only=False, reuse_features: bool = True):
+                          window_ids: Optional[Sequence[int]] = None, raw_only=False, reuse_features: bool = True,
+                          aligner: Optional["WindowAligner"] = None):
         """frames uint8 [N,H0,W0,3] -> (float32 [N,H0,W0], target_fps)   (video_depth.py:166-254).
 
         Everything after the upload of the uint8 frames runs on the device: per-window gather + cv2-style
@@ -106,7 +110,8 @@ class VideoDepthAnything(nn.Module):
         `fp32` is accepted for signature compatibility; operand precision is the engine's dtype (bf16/fp16
         tensor-core operands, fp32 accumulation / residual / statistics).
         `window_ids` / `raw_only` are the multi-GPU hooks (parallel.py): compute only those windows and return
-        the raw, resized per-window depths [len(window_ids),32,H0,W0] on the device, skipping alignment.
+        the raw, resized per-window depths [len(window_ids),32,H0,W0] on the device, skipping alignment; with
+        `aligner` the windows are pushed into that WindowAligner instead (the caller finishes it) and None is returned.
         `reuse_features`: the DINOv2 encoder is per-frame and 10 of a window's 32 slots repeat frames of earlier
         windows (:200-201), so each source frame is encoded once and its four tap features are kept on the device
         until no later window needs them (FeatureCache); every kernel is batch-invariant, so the result is
@@ -124,32 +129,38 @@ class VideoDepthAnything(nn.Module):
         ids = list(range(len(wins))) if window_ids is None else list(window_ids)
         with torch.cuda.device(self._device):
             if not ids:
+                if aligner is not None:
+                    return None
                 return torch.empty(0, INFER_LEN, h0, w0, device=self._device) if raw_only else \
                     (np.empty((0, h0, w0), np.float32), target_fps)
             needed = sorted({i for k in ids for i in wins[k]})
             up = FrameUploader(frames, needed, self._device)
-            raws = []
-            aligner = None if raw_only else WindowAligner(n, h0, w0, self._device,
-                                                          "identity" if self.metric else "affine")
-            cache = FeatureCache(eng, up, nh, nw) if reuse_features else None
-            for k in ids:
+            # raw stack allocated once: a fresh 34 MB block per window costs a cudaMalloc each (~10 ms at 518x518)
+            raws = torch.empty(len(ids), INFER_LEN, h0, w0, dtype=torch.float32, device=self._device) if raw_only else None
+            own_aligner = aligner is None and not raw_only
+            if own_aligner:
+                aligner = WindowAligner(n, h0, w0, self._device, "identity" if self.metric else "affine")
+            cache = FeatureCache(eng, up, nh, nw, [wins[k] for k in ids]) if reuse_features else None
+            if cache is None:     # all index lists in one upload (a per-window pageable H2D would sync the stream)
+                idx_all = torch.tensor([[up.slot[i] for i in wins[k]] for k in ids], dtype=torch.int32).pin_memory() \
+                    .to(self._device, non_blocking=True)
+            for j, k in enumerate(ids):
                 up.ensure(max(wins[k]))                                      # H2D of the chunks this window needs
                 if cache is not None:
-                    d = cache.window(wins[k])                                # [32,nh,nw] fp32 (graph-owned buffer)
+                    d = cache.window(j)                                      # [32,nh,nw] fp32 (graph-owned buffer)
                 else:
-                    idx = torch.tensor([up.slot[i] for i in wins[k]], dtype=torch.int32, device=self._device)
-                    x = ops.preprocess_frames(up.dev, idx, nh, nw).unsqueeze(0)  # [1,32,3,nh,nw]   (:197-201)
+                    x = ops.preprocess_frames(up.dev, idx_all[j], nh, nw).unsqueeze(0)  # [1,32,3,nh,nw]   (:197-201)
                     d = eng.forward(x)[0]                                    # [32,nh,nw] fp32   (:203-205)
                 if (nh, nw) != (h0, w0):
-                    d = ops.bilinear_f32(d, h0, w0)                          # video_depth.py:208
-                elif raw_only and cache is not None:
-                    d = d.clone()
-                if raw_only:
-                    raws.append(d)
-                else:
+                    d = ops.bilinear_f32(d, h0, w0, out=raws[j] if raw_only else None)   # video_depth.py:208
+                elif raw_only:
+                    raws[j].copy_(d)
+                if not raw_only:
                     aligner.push(d)
             if raw_only:
-                return torch.stack(raws)
+                return raws
+            if not own_aligner:
+                return None
             return aligner.result(), target_fps
 
 
@@ -161,35 +172,46 @@ class FeatureCache:
     32 device slots per tap ([slot, P, D] 16-bit); frames the current window does not use are evicted (later
     windows only ever reuse frames of their predecessor)."""
 
-    def __init__(self, eng: Engine, up: "FrameUploader", nh: int, nw: int):
+    def __init__(self, eng: Engine, up: "FrameUploader", nh: int, nw: int, windows: Sequence[Sequence[int]]):
         self.eng, self.up, self.nh, self.nw = eng, up, nh, nw
         self.hp, self.wp = nh // 14, nw // 14
         P = self.hp * self.wp
         self.store = [torch.empty(INFER_LEN, P, eng.D, dtype=eng.dtype, device=eng.device) for _ in range(4)]
-        self.where = {}                                   # source frame -> slot
-        self.free = list(range(INFER_LEN))
         self.encoded = 0                                  # frames that went through the encoder (for reporting)
+        # The slot bookkeeping depends on the window list only, so the index lists of ALL windows are planned on the
+        # host now and uploaded once: per window [uploaded-frame index of each new frame | its cache slot | slot of
+        # each of the 32 window positions].  (A per-window pageable H2D copy synchronises the stream and drains the
+        # GPU between windows.)
+        where, free = {}, list(range(INFER_LEN))          # source frame -> slot
+        table = np.zeros((max(len(windows), 1), 3 * INFER_LEN), dtype=np.int32)
+        self.n_new = []
+        for j, src in enumerate(windows):
+            need = set(src)
+            for f in [f for f in where if f not in need]:
+                free.append(where.pop(f))
+            missing = sorted(need - where.keys())
+            slots = [free.pop() for _ in missing]
+            where.update(zip(missing, slots))
+            n = len(missing)
+            self.n_new.append(n)
+            table[j, :n] = [up.slot[f] for f in missing]
+            table[j, INFER_LEN:INFER_LEN + n] = slots
+            table[j, 2 * INFER_LEN:] = [where[f] for f in src]
+        self.table = torch.from_numpy(table).pin_memory().to(eng.device, non_blocking=True)
 
-    def window(self, src: Sequence[int]) -> torch.Tensor:
-        eng, dev, P = self.eng, self.eng.device, self.hp * self.wp
-        need = set(src)
-        for f in [f for f in self.where if f not in need]:
-            self.free.append(self.where.pop(f))
-        missing = sorted(need - self.where.keys())
-        n = len(missing)
-        slots = [self.free.pop() for _ in missing]
-        self.where.update(zip(missing, slots))
-        lists = torch.tensor([self.up.slot[f] for f in missing] + slots + [self.where[f] for f in src],
-                             dtype=torch.int32, device=dev)     # one small H2D per window
+    def window(self, j: int) -> torch.Tensor:
+        """Depths [32, nh, nw] of the j-th planned window (a graph-owned buffer: consume before the next call)."""
+        eng, P, n = self.eng, self.hp * self.wp, self.n_new[j]
+        row = self.table[j]
         if n:
-            x = ops.preprocess_frames(self.up.dev, lists[:n], self.nh, self.nw)        # [n,3,nh,nw]   (:197-198)
+            x = ops.preprocess_frames(self.up.dev, row[:n], self.nh, self.nw)          # [n,3,nh,nw]   (:197-198)
             taps = eng.encode_frames(x)
             for i in range(4):
-                ops.copy_frames(taps[i].view(n, P, eng.D), None, self.store[i], lists[n:2 * n], n)
+                ops.copy_frames(taps[i].view(n, P, eng.D), None, self.store[i], row[INFER_LEN:INFER_LEN + n], n)
             self.encoded += n
         head_in = eng.head_static_inputs(INFER_LEN, self.hp, self.wp)
         for i in range(4):
-            ops.copy_frames(self.store[i], lists[2 * n:], head_in[i].view(INFER_LEN, P, eng.D), None, INFER_LEN)
+            ops.copy_frames(self.store[i], row[2 * INFER_LEN:], head_in[i].view(INFER_LEN, P, eng.D), None, INFER_LEN)
         return eng.head_frames(head_in, INFER_LEN, self.hp, self.wp)
 
 
@@ -240,8 +262,12 @@ class FrameUploader:
 class WindowAligner:
     """Sequential scale/shift alignment + cross-fade of consecutive windows on the device
     (video_depth.py:216-252, utils/util.py:40-74).  (scale, shift) never leave the GPU; frames that can no longer
-    change (everything but the last 8) are streamed to the host through pinned staging buffers while the next
-    windows compute."""
+    change (everything but the last 8) are streamed to the host while the next windows compute: D2H into pinned
+    staging buffers on a copy stream, and a drain thread (numpy copies release the GIL; large batches are split over
+    a small pool) moves them into the result array, so the launching thread never waits for a host memcpy."""
+
+    STAGES = 4
+    COPY_THREADS = 4
 
     def __init__(self, n_frames: int, h0: int, w0: int, device, mode: str = "affine"):
         self.n, self.h0, self.w0, self.device, self.mode = n_frames, h0, w0, device, mode
@@ -256,26 +282,46 @@ class WindowAligner:
         self.blend_w = torch.tensor([0.0] + [i * step for i in range(1, INTERP_LEN - 1)] + [1.0],
                                     dtype=torch.float32, device=device)
         self.host = np.empty((n_frames, h0, w0), dtype=np.float32)
-        self.stage = [torch.empty(INFER_LEN, h0, w0, dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.pending = [None, None]          # (event, lo, hi) of the D2H copy sitting in each staging buffer
+        self.stage = [torch.empty(INFER_LEN, h0, w0, dtype=torch.float32).pin_memory() for _ in range(self.STAGES)]
+        self.stage_free = [threading.Event() for _ in range(self.STAGES)]
+        for e in self.stage_free:
+            e.set()
         self.copy_stream = torch.cuda.Stream(device=device)
         self.sent = 0                        # frames already handed to the D2H pipeline
         self.batch_no = 0
+        self.jobs: "queue.Queue" = queue.Queue()
+        self.error = None
+        self.pool = ThreadPoolExecutor(self.COPY_THREADS)
+        self.drainer = threading.Thread(target=self._drain_loop, daemon=True)
+        self.drainer.start()
 
-    def _drain(self, b: int) -> None:
-        if self.pending[b] is not None:
-            ev, lo, hi = self.pending[b]
-            ev.synchronize()
-            np.copyto(self.host[lo:hi], self.stage[b][:hi - lo].numpy())
-            self.pending[b] = None
+    def _drain_loop(self) -> None:
+        while True:
+            job = self.jobs.get()
+            if job is None:
+                self.jobs.task_done()
+                return
+            ev, b, lo, hi = job
+            try:
+                ev.synchronize()
+                src = self.stage[b].numpy()
+                cuts = np.linspace(0, hi - lo, self.COPY_THREADS + 1).astype(int)
+                list(self.pool.map(lambda i: np.copyto(self.host[lo + cuts[i]:lo + cuts[i + 1]], src[cuts[i]:cuts[i + 1]]),
+                                   range(self.COPY_THREADS)))
+            except BaseException as e:       # surfaced by result()
+                self.error = e
+            finally:
+                self.stage_free[b].set()
+                self.jobs.task_done()
 
     def _send(self, upto: int) -> None:
         """Stream frames [sent, upto) (final values) to the host."""
         upto = min(upto, self.n)
         while self.sent < upto:
             lo, hi = self.sent, min(self.sent + INFER_LEN, upto)
-            b = self.batch_no & 1
-            self._drain(b)
+            b = self.batch_no % self.STAGES
+            self.stage_free[b].wait()
+            self.stage_free[b].clear()
             ready = torch.cuda.Event()
             ready.record()                                   # the frames are final once the current stream gets here
             with torch.cuda.stream(self.copy_stream):
@@ -283,7 +329,7 @@ class WindowAligner:
                 self.stage[b][:hi - lo].copy_(self.out[lo:hi], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
-            self.pending[b] = (ev, lo, hi)
+            self.jobs.put((ev, b, lo, hi))
             self.sent = hi
             self.batch_no += 1
 
@@ -309,6 +355,10 @@ class WindowAligner:
 
     def result(self) -> np.ndarray:
         self._send(self.n)
-        self._drain(0)
-        self._drain(1)
+        self.jobs.put(None)
+        self.jobs.join()
+        self.drainer.join()
+        self.pool.shutdown()
+        if self.error is not None:
+            raise self.error
         return self.host
