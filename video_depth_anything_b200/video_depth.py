@@ -267,7 +267,7 @@ class WindowAligner:
     a small pool) moves them into the result array, so the launching thread never waits for a host memcpy."""
 
     STAGES = 4
-    COPY_THREADS = 4
+    COPY_THREADS = 6
 
     def __init__(self, n_frames: int, h0: int, w0: int, device, mode: str = "affine"):
         self.n, self.h0, self.w0, self.device, self.mode = n_frames, h0, w0, device, mode
@@ -292,6 +292,12 @@ class WindowAligner:
         self.jobs: "queue.Queue" = queue.Queue()
         self.error = None
         self.pool = ThreadPoolExecutor(self.COPY_THREADS)
+        # first-touch the result array in the background (one write per page): the page faults of a fresh multi-GB
+        # allocation otherwise sit inside the drain copies and halve their bandwidth
+        flat = self.host.reshape(-1)
+        cuts = np.linspace(0, flat.size, self.COPY_THREADS + 1).astype(np.int64)
+        for i in range(self.COPY_THREADS):
+            self.pool.submit(lambda a=flat[cuts[i]:cuts[i + 1]]: a[::1024].fill(0))
         self.drainer = threading.Thread(target=self._drain_loop, daemon=True)
         self.drainer.start()
 
