@@ -53,6 +53,7 @@ struct GemmDev {
   float tail_b;
   int staged;   // LINEAR: transpose the tile through shared memory (fp32 residual / fp32 output streams)
   int pair;     // host only: launch the cta_group::2 variant
+  int prefetch_max_kb;   // residual L2 prefetch of the next tile only when the K loop has at most this many blocks
 };
 
 // 4 consecutive columns as two packed fp32 pairs (FFMA2 / FADD2 / FMUL2 process a pair per instruction)
@@ -337,9 +338,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
         constexpr bool staged = STAGED;
-        if (EPI == VDA_EPI_LINEAR && (p.res1 || p.res2)) {
+        if (EPI == VDA_EPI_LINEAR && (p.res1 || p.res2) && p.num_k_blocks <= p.prefetch_max_kb) {
           // pull the residual rows of this CTA's NEXT tile towards L2 now: its epilogue then reads them at L2
-          // latency instead of queueing behind HBM (the epilogue is a dependent load -> math -> store chain)
+          // latency instead of queueing behind HBM (the epilogue is a dependent load -> math -> store chain).
+          // Only when the next epilogue is near (short K loop): with K = 4096 it is ~20 us away and the streaming
+          // traffic of the kernel evicts most prefetched lines first (fc2: 185 MB of excess DRAM reads per launch)
           const int nxt = tile + tile_step;
           if (nxt < p.num_tiles) {
             const int n_blk2 = nxt % p.tiles_n;
@@ -543,6 +546,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int c0 = c_begin; c0 < c_end; c0 += 32) {
             const bool wide = c0 + 32 <= c_end;                            // 32 columns, else the last 16
             // ---- phase 1: accumulators (thread = row) -> swizzled staging tile ----
+            // (issuing the tcgen05.ld of chunk c+1 before chunk c's math was tried: the 32 extra live registers push
+            // the kernel over its 168-register cap and the spills cost more than the hidden latency: proj 115 -> 125 us)
             {
               uint32_t rr[32];
               if (wide) {
@@ -850,6 +855,10 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
   GemmDev d = {};
   d.M = p->M; d.N = p->N; d.K = p->K;
   d.num_k_blocks = (p->K + BLOCK_K - 1) / BLOCK_K;
+  {
+    static const char* pf = getenv("VDA_GEMM_PREFETCH_KB");     // debug hook (tools/bench_gemm.py)
+    d.prefetch_max_kb = pf ? atoi(pf) : 32;
+  }
   CUtensorMap tmA, tmB;
 
   if (conv) {

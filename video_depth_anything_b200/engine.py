@@ -190,6 +190,14 @@ class Engine:
                 self._pos_cache[key] = ops.pos_embed_bicubic(pos, hp, wp)
         return self._pos_cache[key]
 
+    def _const(self, value: float, n: int) -> torch.Tensor:
+        """Cached fp32 constant vector (zero bias / unit LayerScale that route a GEMM to a compile-time specialised
+        epilogue; adding 0 and multiplying by 1 are exact)."""
+        key = ("const", value, n)
+        if key not in self._bufs:
+            self._bufs[key] = [torch.full((n,), value, dtype=torch.float32, device=self.device)]
+        return self._bufs[key][0]
+
     def _new(self, *shape, dtype=None):
         return torch.empty(*shape, dtype=dtype or self.dtype, device=self.device)
 
@@ -281,11 +289,11 @@ class Engine:
         for a in (0, 1):                                                                # :165-172
             ops.layernorm(h, w[f"{p}a{a}.ln.w"], w[f"{p}a{a}.ln.b"], 1e-5, n, pe=w[f"{p}a{a}.pe"], pe_rows_per_frame=hw,
                           pe_frames=T)                     # rows are (clip, frame, position): frame = (r // hw) % T
-            ops.gemm(n, w[f"{p}a{a}.qkv.w"], qkv)
+            ops.gemm(n, w[f"{p}a{a}.qkv.w"], qkv, bias=self._const(0.0, 3 * C))   # zero bias: takes the specialised epilogue
             for b in range(B):
                 s = slice(b * T * hw, (b + 1) * T * hw)
                 ops.attention_temporal(qkv[s], o[s], T, hw, C)
-            ops.gemm(o, w[f"{p}a{a}.o.w"], h, bias=w[f"{p}a{a}.o.b"], res1=h)
+            ops.gemm(o, w[f"{p}a{a}.o.w"], h, bias=w[f"{p}a{a}.o.b"], gamma=self._const(1.0, C), res1=h)   # unit LayerScale: ditto
         ops.layernorm(h, w[p + "ffn.w"], w[p + "ffn.b"], 1e-5, n)                        # :174
         g = self._new(M, 4 * C)
         ops.gemm(n, w[p + "ff0.w"], g, bias=w[p + "ff0.b"], epilogue=EPI_GEGLU, geglu_half=self.mm_half[m])
