@@ -29,13 +29,16 @@ def main():
     m.to(f"cuda:{local}")
     n = int(os.environ.get("VDA_FRAMES", "100"))
     frames = np.random.default_rng(0).integers(0, 256, (n, 98, 126, 3), dtype=np.uint8)
-    out, _ = infer_video_depth_sharded(m, frames, 24, input_size=98)
-    if rank == 0:
-        ref, _ = m.infer_video_depth(frames, 24, input_size=98, device=f"cuda:{local}")
-        same = np.array_equal(out, ref)
-        print(f"multi_gpu_check: world {dist.get_world_size()} frames {n} windows {-(-n // 22)}: "
-              f"{'bit-identical' if same else 'MISMATCH max abs ' + str(np.abs(out - ref).max())}", flush=True)
-        assert same
+    ref = m.infer_video_depth(frames, 24, input_size=98, device=f"cuda:{local}")[0] if rank == 0 else None
+    for mode in ("two_phase", "stream"):          # shared-memory two-phase form and the rank-0 streaming form
+        os.environ["VDA_SHARD_MODE"] = mode
+        out, _ = infer_video_depth_sharded(m, frames, 24, input_size=98)
+        if rank == 0:
+            same = np.array_equal(out, ref)
+            print(f"multi_gpu_check[{mode}]: world {dist.get_world_size()} frames {n} windows {-(-n // 22)}: "
+                  f"{'bit-identical' if same else 'MISMATCH max abs ' + str(np.abs(out - ref).max())}", flush=True)
+            assert same
+        dist.barrier()
     dist.barrier()
     dist.destroy_process_group()
 

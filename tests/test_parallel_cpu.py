@@ -113,3 +113,13 @@ def test_stream_collect_matches_single_process(tmp_path, world, n_frames):
     got = np.load(out)
     ref = torch.stack([fake_raw(i) for i in range(num_windows(n_frames))]).numpy()
     assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_frame_spans_tile_the_video():
+    """Two-phase driver: the frames finalised by each rank's block of windows partition [0, n) in rank order."""
+    from video_depth_anything_b200.parallel import frame_span
+    for n in (1, 23, 45, 70, 100, 131, 2048):
+        K = num_windows(n)
+        for world in (1, 2, 3, 8):
+            spans = [frame_span(p[0], p[-1] + 1, K, n) if len(p) else (0, 0) for p in partition_windows(K, world)]
+            assert [f for lo, hi in spans for f in range(lo, hi)] == list(range(n)), (n, world, spans)

@@ -20,7 +20,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .windows import INFER_LEN, num_windows
+from .windows import INFER_LEN, INTERP_LEN, KEYFRAMES, OVERLAP, STEP, num_windows
+
+KEYFRAME_REF = KEYFRAMES[1]           # slot 12: the frame whose aligned depth becomes the next window's reference
 
 
 def partition_windows(n_windows: int, world: int) -> List[range]:
@@ -92,6 +94,149 @@ def stream_window_depths(local: Optional[torch.Tensor], counts: Sequence[int], s
         yield r, bufs[r]
 
 
+def frame_span(k0: int, k1: int, n_windows: int, n_frames: int):
+    """Video frames finalised by the rank that owns windows [k0, k1): window k's slots 2..9 are cross-faded with the
+    previous window's slots 24..31 and become frames 22k+2..22k+9, its slots 10..31 become frames 22k+10..22k+31, of
+    which the last 8 are re-blended (and finalised) by window k+1 (video_depth.py:216-252).  Returns [lo, hi)."""
+    if k1 <= k0:
+        return 0, 0
+    lo = 0 if k0 == 0 else STEP * k0 + 2
+    hi = STEP * k1 + 2 if k1 < n_windows else STEP * (n_windows - 1) + INFER_LEN
+    return min(lo, n_frames), min(hi, n_frames)
+
+
+def _same_host(group) -> bool:
+    import socket
+    names = [None] * dist.get_world_size(group)
+    dist.all_gather_object(names, socket.gethostname(), group=group)
+    return len(set(names)) == 1
+
+
+@torch.no_grad()
+def _infer_two_phase(model, frames, target_fps, input_size, device, group):
+    """Scalable form for one node (SURVEY.md §8e option 2).  Every rank computes its block of windows; the three
+    anchor frames of every window (slots 0, 1, 12) are all-gathered and every rank runs the tiny sequential
+    scale/shift recurrence itself (same kernels, same order as WindowAligner.push, so the result is bit-identical);
+    then each rank clamps / cross-fades ITS frames (one 8-frame halo from the left neighbour) and downloads them
+    into a POSIX shared-memory array owned by rank 0 -- PCIe, host copies and page faults are spread over all
+    ranks instead of funnelled through one."""
+    from multiprocessing import resource_tracker, shared_memory
+    from . import ops
+    from .video_depth import HostDrain, make_blend_weights
+    rank, world = _world(group)
+    dev = torch.device(device)
+    n, h0, w0 = frames.shape[:3]
+    K = num_windows(n)
+    parts = partition_windows(K, world)
+    counts = [len(p) for p in parts]
+    k0, k1 = (parts[rank][0], parts[rank][-1] + 1) if counts[rank] else (0, 0)
+    lo, hi = frame_span(k0, k1, K, n)
+    # shared result array: created by rank 0, attached by the others, first-touched per slice in the background
+    nbytes = n * h0 * w0 * 4
+    box = [None]
+    if rank == 0:
+        shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        box[0] = shm.name
+    dist.broadcast_object_list(box, src=0, group=group)
+    if rank != 0:
+        shm = shared_memory.SharedMemory(name=box[0])
+        resource_tracker.unregister(shm._name, "shared_memory")     # rank 0 owns the segment's lifetime
+    host = np.ndarray((n, h0, w0), dtype=np.float32, buffer=shm.buf)
+    trace = os.environ.get("VDA_TRACE_VIDEO") == "1"
+    stamps = [("start", time.perf_counter())]
+
+    def stamp(name):
+        if trace:
+            torch.cuda.synchronize(dev)
+            stamps.append((name, time.perf_counter()))
+
+    with torch.cuda.device(dev):
+        stamp("shm ready")
+        drain = HostDrain(host, dev, touch=slice(lo, hi))
+        raws = model.infer_video_depth(frames, target_fps, input_size=input_size, device=dev,
+                                       window_ids=list(parts[rank]), raw_only=True)          # [k_r,32,h0,w0]
+        stamp("windows computed")
+        # ---- anchors -> (scale, shift) of every window, on every rank ----
+        kmax = max(counts)
+        mine = torch.zeros(kmax, 3, h0, w0, dtype=torch.float32, device=dev)
+        if counts[rank]:
+            mine[:counts[rank]].copy_(raws[:, [0, 1, KEYFRAME_REF]])
+        gathered = torch.empty(world, kmax, 3, h0, w0, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+        anchors = torch.cat([gathered[r, :counts[r]] for r in range(world)])                  # [K,3,h0,w0]
+        table = torch.empty(K, 2, dtype=torch.float32, device=dev)
+        ss = torch.tensor([1.0, 0.0], dtype=torch.float32, device=dev)
+        table[0].copy_(ss)
+        scratch = torch.zeros(4 * ops.LSQ_MAX_PARTIALS, dtype=torch.float64, device=dev)
+        ref = torch.stack([anchors[0, 0], anchors[0, 2]])
+        for k in range(1, K):
+            if not model.metric:
+                ops.lsq_scale_shift(anchors[k, 0:2], ref, ss, scratch)                        # video_depth.py:227-232
+            table[k].copy_(ss)
+            ops.affine_clamp_blend(anchors[k, 2:3], ss, ref[1:2])                             # :246-250
+        stamp("scale/shift table")
+        # ---- halo: raw slots 24..31 of the window before my first one ----
+        reqs, halo = [], None
+        owners = [r for r in range(world) if counts[r]]
+        if counts[rank]:
+            i = owners.index(rank)
+            if i + 1 < len(owners):
+                reqs.append(dist.P2POp(dist.isend, raws[-1, INFER_LEN - INTERP_LEN:].contiguous(), owners[i + 1], group))
+            if i > 0:
+                halo = torch.empty(INTERP_LEN, h0, w0, dtype=torch.float32, device=dev)
+                reqs.append(dist.P2POp(dist.irecv, halo, owners[i - 1], group))
+        if reqs:
+            for w in dist.batch_isend_irecv(reqs):
+                w.wait()
+        # ---- my frames: same kernel sequence as WindowAligner.push with the tabulated (scale, shift), in place in the
+        #      raw stack (the kernels are elementwise): window j's slots 2..9 are cross-faded with the aligned slots
+        #      24..31 of window j-1, slots 10..31 are aligned; its slots [2, 24) are then final video frames
+        #      22k+2 .. 22k+23 and go to the host at once (the last window keeps its slots 24..31 too) ----
+        if counts[rank]:
+            blend_w = make_blend_weights(dev)
+            for j in range(k1 - k0):
+                k, d = k0 + j, raws[j]
+                if k == 0:                                                   # window 0 is copied unclamped (:222-225)
+                    first = 0
+                else:
+                    ssk = table[k]
+                    if j > 0:
+                        prev = raws[j - 1, INFER_LEN - INTERP_LEN:]          # already aligned in place
+                    elif k == 1:
+                        prev = halo                                          # window 0's frames: never scaled or clamped
+                    else:
+                        prev = ops.affine_clamp_blend(halo, table[k - 1], halo)
+                    head = d[OVERLAP - INTERP_LEN:OVERLAP]
+                    ops.affine_clamp_blend(head, ssk, head, prev=prev, blend_w=blend_w)            # :234-239
+                    ops.affine_clamp_blend(d[OVERLAP:], ssk, d[OVERLAP:])                          # :241-244
+                    first = OVERLAP - INTERP_LEN
+                last = INFER_LEN if k == K - 1 else INFER_LEN - INTERP_LEN
+                f0 = STEP * k + first
+                f1 = min(STEP * k + last, n)
+                if f1 > f0:
+                    drain.send(d[first:first + f1 - f0], f0)
+            stamp("frames blended")
+        drain.finish()
+        stamp("downloaded")
+    dist.barrier(group=group)
+    stamp("barrier")
+    if trace:
+        print(f"video trace rank {rank}: " + ", ".join(f"{a} +{(t - stamps[0][1]) * 1e3:.0f} ms" for a, t in stamps[1:]), flush=True)
+    if rank != 0:
+        del host, drain
+        try:
+            shm.close()
+        except BufferError:           # a view is still referenced somewhere: the mapping goes away with the process
+            pass
+        return None, target_fps
+    shm.unlink()                      # the name goes away now; the mapping lives as long as the returned array
+    _LIVE_SEGMENTS.append(shm)
+    return host, target_fps
+
+
+_LIVE_SEGMENTS: list = []             # shared-memory segments backing arrays handed to the caller
+
+
 @torch.no_grad()
 def infer_video_depth_sharded(model, frames: np.ndarray, target_fps, input_size: int = 518, device=None,
                               dst: int = 0, group=None):
@@ -107,6 +252,11 @@ def infer_video_depth_sharded(model, frames: np.ndarray, target_fps, input_size:
     n, h0, w0 = frames.shape[:3]
     parts = partition_windows(num_windows(n), world)
     counts = [len(p) for p in parts]
+    # two-phase (every rank downloads its own frames into shared memory) pays from 4 ranks on; with 2 ranks the
+    # streaming form wins because rank 0 downloads its half while it computes (measured 2.10 vs 2.27 s, 2048 frames)
+    mode = os.environ.get("VDA_SHARD_MODE", "two_phase" if world >= 4 else "stream")
+    if dst == 0 and min(counts) > 0 and mode == "two_phase" and _same_host(group):
+        return _infer_two_phase(model, frames, target_fps, input_size, device, group)
     if dst == 0:
         # streaming form: rank 0 owns the first block of windows, so it aligns them (and streams the finished frames
         # to the host) while it computes; the other ranks' stacks arrive point-to-point and are aligned in rank order
@@ -159,4 +309,5 @@ def infer_video_depth_sharded(model, frames: np.ndarray, target_fps, input_size:
         return aligner.result(), target_fps
 
 
-__all__ = ["partition_windows", "gather_window_depths", "stream_window_depths", "infer_video_depth_sharded", "INFER_LEN"]
+__all__ = ["partition_windows", "gather_window_depths", "stream_window_depths", "frame_span", "infer_video_depth_sharded",
+           "INFER_LEN"]

@@ -259,42 +259,29 @@ class FrameUploader:
             torch.cuda.current_stream().wait_event(last_ev)
 
 
-class WindowAligner:
-    """Sequential scale/shift alignment + cross-fade of consecutive windows on the device
-    (video_depth.py:216-252, utils/util.py:40-74).  (scale, shift) never leave the GPU; frames that can no longer
-    change (everything but the last 8) are streamed to the host while the next windows compute: D2H into pinned
-    staging buffers on a copy stream, and a drain thread (numpy copies release the GIL; large batches are split over
-    a small pool) moves them into the result array, so the launching thread never waits for a host memcpy."""
+class HostDrain:
+    """Device -> host streaming of finished fp32 frames: D2H into pinned staging buffers on a copy stream, and a drain
+    thread (numpy copies release the GIL; every batch is split over a small pool) moves them into the result array,
+    so the launching thread never waits for a host memcpy.  The result array is first-touched in the background (one
+    write per page): the page faults of a fresh multi-GB allocation otherwise sit inside the drain copies and divide
+    their bandwidth by ~5 (tools/microbench/host_touch.py)."""
 
     STAGES = 4
     COPY_THREADS = 6
 
-    def __init__(self, n_frames: int, h0: int, w0: int, device, mode: str = "affine"):
-        self.n, self.h0, self.w0, self.device, self.mode = n_frames, h0, w0, device, mode
-        k = -(-n_frames // (INFER_LEN - OVERLAP))
-        total = k * (INFER_LEN - OVERLAP) + OVERLAP
-        self.out = torch.empty(total, h0, w0, dtype=torch.float32, device=device)
-        self.filled = 0
-        self.ref = None                      # [2,h0,w0]: (ref_align[0], ref_align[1])
-        self.ss = torch.tensor([1.0, 0.0], dtype=torch.float32, device=device)
-        self.scratch = torch.zeros(4 * ops.LSQ_MAX_PARTIALS, dtype=torch.float64, device=device)
-        step = 1.0 / (INTERP_LEN - 1)
-        self.blend_w = torch.tensor([0.0] + [i * step for i in range(1, INTERP_LEN - 1)] + [1.0],
-                                    dtype=torch.float32, device=device)
-        self.host = np.empty((n_frames, h0, w0), dtype=np.float32)
+    def __init__(self, host: np.ndarray, device, touch: Optional[slice] = None):
+        self.host, self.device = host, device
+        h0, w0 = host.shape[1:]
         self.stage = [torch.empty(INFER_LEN, h0, w0, dtype=torch.float32).pin_memory() for _ in range(self.STAGES)]
         self.stage_free = [threading.Event() for _ in range(self.STAGES)]
         for e in self.stage_free:
             e.set()
         self.copy_stream = torch.cuda.Stream(device=device)
-        self.sent = 0                        # frames already handed to the D2H pipeline
         self.batch_no = 0
         self.jobs: "queue.Queue" = queue.Queue()
         self.error = None
         self.pool = ThreadPoolExecutor(self.COPY_THREADS)
-        # first-touch the result array in the background (one write per page): the page faults of a fresh multi-GB
-        # allocation otherwise sit inside the drain copies and halve their bandwidth
-        flat = self.host.reshape(-1)
+        flat = (host if touch is None else host[touch]).reshape(-1)
         cuts = np.linspace(0, flat.size, self.COPY_THREADS + 1).astype(np.int64)
         for i in range(self.COPY_THREADS):
             self.pool.submit(lambda a=flat[cuts[i]:cuts[i + 1]]: a[::1024].fill(0))
@@ -314,30 +301,68 @@ class WindowAligner:
                 cuts = np.linspace(0, hi - lo, self.COPY_THREADS + 1).astype(int)
                 list(self.pool.map(lambda i: np.copyto(self.host[lo + cuts[i]:lo + cuts[i + 1]], src[cuts[i]:cuts[i + 1]]),
                                    range(self.COPY_THREADS)))
-            except BaseException as e:       # surfaced by result()
+            except BaseException as e:       # surfaced by finish()
                 self.error = e
             finally:
                 self.stage_free[b].set()
                 self.jobs.task_done()
 
-    def _send(self, upto: int) -> None:
-        """Stream frames [sent, upto) (final values) to the host."""
-        upto = min(upto, self.n)
-        while self.sent < upto:
-            lo, hi = self.sent, min(self.sent + INFER_LEN, upto)
+    def send(self, frames: torch.Tensor, host_lo: int) -> None:
+        """Queue device frames [m,h0,w0] (final once the current stream gets here) for host rows [host_lo, host_lo+m)."""
+        for off in range(0, frames.shape[0], INFER_LEN):
+            part = frames[off:off + INFER_LEN]
             b = self.batch_no % self.STAGES
             self.stage_free[b].wait()
             self.stage_free[b].clear()
             ready = torch.cuda.Event()
-            ready.record()                                   # the frames are final once the current stream gets here
+            ready.record()
             with torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(ready)
-                self.stage[b][:hi - lo].copy_(self.out[lo:hi], non_blocking=True)
+                self.stage[b][:part.shape[0]].copy_(part, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
-            self.jobs.put((ev, b, lo, hi))
-            self.sent = hi
+            self.jobs.put((ev, b, host_lo + off, host_lo + off + part.shape[0]))
             self.batch_no += 1
+
+    def finish(self) -> np.ndarray:
+        self.jobs.put(None)
+        self.jobs.join()
+        self.drainer.join()
+        self.pool.shutdown()
+        if self.error is not None:
+            raise self.error
+        return self.host
+
+
+def make_blend_weights(device) -> torch.Tensor:
+    step = 1.0 / (INTERP_LEN - 1)                         # get_interpolate_frames (utils/util.py:65-74)
+    return torch.tensor([0.0] + [i * step for i in range(1, INTERP_LEN - 1)] + [1.0], dtype=torch.float32, device=device)
+
+
+class WindowAligner:
+    """Sequential scale/shift alignment + cross-fade of consecutive windows on the device
+    (video_depth.py:216-252, utils/util.py:40-74).  (scale, shift) never leave the GPU; frames that can no longer
+    change (everything but the last 8) are streamed to the host (HostDrain) while the next windows compute."""
+
+    def __init__(self, n_frames: int, h0: int, w0: int, device, mode: str = "affine"):
+        self.n, self.h0, self.w0, self.device, self.mode = n_frames, h0, w0, device, mode
+        k = -(-n_frames // (INFER_LEN - OVERLAP))
+        total = k * (INFER_LEN - OVERLAP) + OVERLAP
+        self.out = torch.empty(total, h0, w0, dtype=torch.float32, device=device)
+        self.filled = 0
+        self.ref = None                      # [2,h0,w0]: (ref_align[0], ref_align[1])
+        self.ss = torch.tensor([1.0, 0.0], dtype=torch.float32, device=device)
+        self.scratch = torch.zeros(4 * ops.LSQ_MAX_PARTIALS, dtype=torch.float64, device=device)
+        self.blend_w = make_blend_weights(device)
+        self.drain = HostDrain(np.empty((n_frames, h0, w0), dtype=np.float32), device)
+        self.sent = 0                        # frames already handed to the D2H pipeline
+
+    def _send(self, upto: int) -> None:
+        """Stream frames [sent, upto) (final values) to the host."""
+        upto = min(upto, self.n)
+        if upto > self.sent:
+            self.drain.send(self.out[self.sent:upto], self.sent)
+            self.sent = upto
 
     def push(self, d: torch.Tensor) -> None:
         """d: raw depths of the next window, fp32 [32,h0,w0]."""
@@ -361,10 +386,4 @@ class WindowAligner:
 
     def result(self) -> np.ndarray:
         self._send(self.n)
-        self.jobs.put(None)
-        self.jobs.join()
-        self.drainer.join()
-        self.pool.shutdown()
-        if self.error is not None:
-            raise self.error
-        return self.host
+        return self.drain.finish()
