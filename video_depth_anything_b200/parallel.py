@@ -252,9 +252,12 @@ def infer_video_depth_sharded(model, frames: np.ndarray, target_fps, input_size:
     n, h0, w0 = frames.shape[:3]
     parts = partition_windows(num_windows(n), world)
     counts = [len(p) for p in parts]
-    # two-phase (every rank downloads its own frames into shared memory) pays from 4 ranks on; with 2 ranks the
-    # streaming form wins because rank 0 downloads its half while it computes (measured 2.10 vs 2.27 s, 2048 frames)
-    mode = os.environ.get("VDA_SHARD_MODE", "two_phase" if world >= 4 else "stream")
+    # Default: the streaming form.  Measured on 2048 x 518 x 518 frames: 2 GPUs 2.10 s either way; 8 GPUs 0.64 s
+    # streaming vs 0.75 s two-phase -- rank 0 downloads its own block while it computes and pulls the other 1.9 GB in
+    # ~70 ms, while the two-phase form ran its window phase ~100 ms slower with 8 ranks (48 page-touching / copy
+    # threads on the box's 24 cores next to the launch threads) for the same ~70 ms tail.  The two-phase form
+    # (VDA_SHARD_MODE=two_phase) is kept for larger frames / longer videos, where rank 0's PCIe link becomes the limit.
+    mode = os.environ.get("VDA_SHARD_MODE", "stream")
     if dst == 0 and min(counts) > 0 and mode == "two_phase" and _same_host(group):
         return _infer_two_phase(model, frames, target_fps, input_size, device, group)
     if dst == 0:
