@@ -97,6 +97,11 @@ def test_full_size_window_vs_oracle(enc, dtype, tol):
     fin, rows, d, ref = stage_report(enc, 0, (1, 32, 3, 518, 518), 1234, dtype, oracle_device="cuda")
     assert (ref > 0).float().mean() > 0.99
     _check(dtype, *fin, f"{enc} 1x32x518x518")
+    if enc == "vitl" and dtype == torch.float16:
+        # north_star's validation bar: <= 1e-3 against the fp32 reference with fp32 accumulation.  fp16 operands +
+        # fp32 accumulators / residual stream / statistics is that mode here (8.9e-4 on the headline window; the
+        # forward is bit-reproducible, so this is not a flaky margin)
+        assert fin[0] <= 1e-3, fin
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])
