@@ -102,6 +102,25 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 d = __fadd2_rn(make_float2(exp2f(t.x), exp2f(t.y)), make_float2(1.f, 1.f));
   return __fmul2_rn(x, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
 }
+// Same GELU through one MUFU per element: x Phi(x) = 0.5 x (1 + tanh(u)), u = 0.5 x q(x^2) (sigmoid(2u) = (1 + tanh u) / 2).
+// `tanh.approx.f32` carries a relative error of 2^-11, a quarter of a bf16 output ulp -- used for bf16 outputs only (it
+// would double the rounding noise of fp16 outputs, which have 11 mantissa bits themselves).  6 packed ops + 2 MUFU per pair.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  // coefficients of gelu_erf2's q times -1 / (2 log2 e): u = 0.5 x q_e(x^2) in natural units
+  float2 q = __ffma2_rn(make_float2(1.140916610e-06f, 1.140916610e-06f), x2, make_float2(-3.095375195e-05f, -3.095375195e-05f));
+  q = __ffma2_rn(q, x2, make_float2(-1.229700730e-04f, -1.229700730e-04f));
+  q = __ffma2_rn(q, x2, make_float2(3.646570705e-02f, 3.646570705e-02f));
+  q = __ffma2_rn(q, x2, make_float2(7.978291900e-01f, 7.978291900e-01f));
+  const float2 u = __fmul2_rn(q, x);
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(h, make_float2(tanh_approx(u.x), tanh_approx(u.y)), h);
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

@@ -102,7 +102,11 @@ __device__ __forceinline__ F4 relu4(const F4& x) {
   r.b = make_float2(fmaxf(x.b.x, 0.f), fmaxf(x.b.y, 0.f));
   return r;
 }
+template <typename T>
 __device__ __forceinline__ F4 gelu4(const F4& x) {
+  // (a one-MUFU variant through tanh.approx -- gelu_tanh2 in common.cuh -- was measured for bf16 outputs: fc1 274 -> 266 us
+  // in step, but 1 + tanh(u) cancels for negative inputs and the 2^-11 error of MUFU.TANH raised the bf16 end-to-end
+  // p99.9 error by up to 18 %; the sigmoid form keeps full relative accuracy in the tail and stays)
   F4 r;
   r.a = gelu_erf2(x.a);
   r.b = gelu_erf2(x.b);
@@ -440,7 +444,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (p.bias) v[i] = add4(v[i], load4f(p.bias + co + 4 * i));
               if (EPI == VDA_EPI_LINEAR) {
                 if (p.gamma) v[i] = mul4(v[i], load4f(p.gamma + col + 4 * i));
-                if (p.act == VDA_ACT_GELU) v[i] = gelu4(v[i]);
+                if (p.act == VDA_ACT_GELU) v[i] = gelu4<T>(v[i]);
                 else if (p.act == VDA_ACT_RELU) v[i] = relu4(v[i]);
                 if (p.res1) v[i] = add4(v[i], r1[i]);
                 if (p.res2) v[i] = add4(v[i], r2[i]);
@@ -584,7 +588,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
               if (act == VDA_ACT_GELU) {
 #pragma unroll
-                for (int it = 0; it < 8; ++it) v[it] = gelu4(v[it]);
+                for (int it = 0; it < 8; ++it) v[it] = gelu4<T>(v[it]);
               } else if (act == VDA_ACT_RELU) {
 #pragma unroll
                 for (int it = 0; it < 8; ++it) v[it] = relu4(v[it]);
@@ -667,7 +671,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                   v[it] = add4(v[it], b4);
-                  if (pass == 0) gl[it] = gelu4(v[it]);
+                  if (pass == 0) gl[it] = gelu4<T>(v[it]);
                   else v[it] = mul4(v[it], gl[it]);
                 }
                 if (pass == 1) {
