@@ -107,7 +107,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   x.y = fmaxf(x.y, -126.f);
   const float2 t = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));          // 1.5 * 2^23: integer part in the low bits
   const float2 j = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
-  const float2 f = __fadd2_rn(x, make_float2(-j.x, -j.y));
+  const float2 f = __ffma2_rn(j, make_float2(-1.f, -1.f), x);   // x - j in one packed op (a negated operand costs two scalar FADDs)
   float2 q = __ffma2_rn(make_float2(5.508868381e-02f, 5.508868381e-02f), f, make_float2(2.426040515e-01f, 2.426040515e-01f));
   q = __ffma2_rn(q, f, make_float2(6.932762417e-01f, 6.932762417e-01f));
   q = __ffma2_rn(q, f, make_float2(9.999289404e-01f, 9.999289404e-01f));
