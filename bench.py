@@ -64,7 +64,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop_ev.wait(0.2)
+            self._stop_ev.wait(0.05)   # (one nvidia-smi query takes ~50-100 ms itself: a few samples per second of load)
 
     def stop(self):
         self._stop_ev.set()
