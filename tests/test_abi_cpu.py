@@ -82,3 +82,27 @@ def test_windows_match_oracle():
         assert Wn.window_source_indices(n) == O.window_source_indices_literal(n)
     for hw in ((518, 518), (720, 1280), (60, 80), (1080, 1920), (480, 2000), (2000, 480)):
         assert Wn.get_resize_hw(*hw, 518) == O.get_resize_hw(*hw, 518)
+
+
+def test_feature_cache_plan_properties():
+    """Host logic of the encoder-feature reuse (windows.plan_feature_cache): replaying the plan on a fake slot store gives
+    every window position the features of its own source frame; contiguous window runs encode every frame exactly once;
+    arbitrary window subsets (multi-GPU blocks, non-contiguous ids) stay correct; never more than 32 slots."""
+    from video_depth_anything_b200 import windows as Wn
+    for n in (1, 5, 31, 32, 33, 70, 131, 2048):
+        wins = Wn.window_source_indices(n)
+        for ids in (list(range(len(wins))), list(range(len(wins) // 2, len(wins))), list(range(0, len(wins), 3))):
+            if not ids:
+                continue
+            seq = [wins[k] for k in ids]
+            store, encoded = {}, []
+            for (missing, slots, positions), src in zip(Wn.plan_feature_cache(seq), seq):
+                assert len(set(slots)) == len(slots) and all(0 <= s < Wn.INFER_LEN for s in slots)
+                for f, s in zip(missing, slots):
+                    store[s] = f                      # "encode frame f into slot s"
+                encoded += missing
+                assert [store[s] for s in positions] == list(src)
+            if ids == list(range(ids[0], ids[0] + len(ids))):          # contiguous run: nothing is encoded twice
+                assert len(encoded) == len(set(encoded)) == len({f for w in seq for f in w})
+    steady = Wn.plan_feature_cache(Wn.window_source_indices(200))
+    assert [len(m) for m, _, _ in steady][:4] == [32, 22, 22, 22]

@@ -23,7 +23,8 @@ import torch.nn as nn
 from . import ops
 from .engine import Engine
 from .synth import ENCODER_DIMS, synth_state_dict
-from .windows import INFER_LEN, INTERP_LEN, KEYFRAMES, OVERLAP, get_resize_hw, window_source_indices
+from .windows import (INFER_LEN, INTERP_LEN, KEYFRAMES, OVERLAP, get_resize_hw, plan_feature_cache,
+                      window_source_indices)
 
 
 class VideoDepthAnything(nn.Module):
@@ -182,21 +183,14 @@ class FeatureCache:
         # host now and uploaded once: per window [uploaded-frame index of each new frame | its cache slot | slot of
         # each of the 32 window positions].  (A per-window pageable H2D copy synchronises the stream and drains the
         # GPU between windows.)
-        where, free = {}, list(range(INFER_LEN))          # source frame -> slot
         table = np.zeros((max(len(windows), 1), 3 * INFER_LEN), dtype=np.int32)
         self.n_new = []
-        for j, src in enumerate(windows):
-            need = set(src)
-            for f in [f for f in where if f not in need]:
-                free.append(where.pop(f))
-            missing = sorted(need - where.keys())
-            slots = [free.pop() for _ in missing]
-            where.update(zip(missing, slots))
+        for j, (missing, slots, positions) in enumerate(plan_feature_cache(windows)):
             n = len(missing)
             self.n_new.append(n)
             table[j, :n] = [up.slot[f] for f in missing]
             table[j, INFER_LEN:INFER_LEN + n] = slots
-            table[j, 2 * INFER_LEN:] = [where[f] for f in src]
+            table[j, 2 * INFER_LEN:] = positions
         self.table = torch.from_numpy(table).pin_memory().to(eng.device, non_blocking=True)
 
     def window(self, j: int) -> torch.Tensor:

@@ -78,3 +78,22 @@ def preprocess_frames(frames: np.ndarray, indices: Iterable[int], input_size: in
         img = (img - _MEAN) / _STD
         out[j] = np.transpose(img, (2, 0, 1))
     return out
+
+
+def plan_feature_cache(windows, n_slots: int = INFER_LEN):
+    """Slot bookkeeping of the encoder-feature cache for a sequence of windows (lists of source frames): frames the
+    current window does not use are evicted (a window only ever reuses frames of its predecessor), frames not cached yet
+    get free slots.  Returns, per window, (new_frames, their_slots, slot_of_each_window_position).  Pure host logic
+    (the device side is video_depth.FeatureCache); at most `n_slots` frames are live because a window has 32 slots."""
+    where, free, plan = {}, list(range(n_slots)), []
+    for src in windows:
+        need = set(src)
+        for f in [f for f in where if f not in need]:
+            free.append(where.pop(f))
+        missing = sorted(need - where.keys())
+        if len(missing) > len(free):
+            raise ValueError("feature cache too small for this window")
+        slots = [free.pop() for _ in missing]
+        where.update(zip(missing, slots))
+        plan.append((missing, slots, [where[f] for f in src]))
+    return plan
