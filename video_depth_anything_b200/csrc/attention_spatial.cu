@@ -126,6 +126,7 @@ template <typename T>
 __global__ void __launch_bounds__(sa::THREADS, 1)
 spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaParams p) {
   using namespace sa;
+  pdl_trigger();   // the proj GEMM that follows (launched with the PDL attribute) may be scheduled as our CTAs retire
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full[2], q_empty[2];
   __shared__ __align__(8) uint64_t k_full[KS], k_empty[KS], v_full[VS], v_empty[VS];

@@ -172,6 +172,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_before();
   if (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  // PDL: everything above (barriers, TMEM, descriptor prefetch) may run under the tail of the previous kernel; nothing
+  // below may start before its results are visible.  Our own successor may be scheduled as our CTAs retire.
+  pdl_trigger();
+  pdl_wait();
   const uint32_t tmem_base = tmem_base_s;
   const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;
   // persistent tile loop: a CTA pair shares tile index, CTA r takes m block 2*pair + r
@@ -776,27 +780,34 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev
     VDA_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_smem = smem;
   }
+  const bool pdl = pdl_enabled();
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
   if (!CTA2) {
-    const int grid = d.num_tiles < sm_count() ? d.num_tiles : sm_count();
-    kfn<<<grid, kThreads, smem, st>>>(tmA, tmB, d);
+    cfg.gridDim = dim3(d.num_tiles < sm_count() ? d.num_tiles : sm_count());
   } else {
     // CTA pairs: clusters of 2 (same TPC), one tile pair per cluster and round
     int pairs = sm_count() / 2;
     if (d.num_tiles < pairs) pairs = d.num_tiles;
-    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    VDA_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, d));
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (pdl) {   // programmatic dependent launch: our prologue overlaps the predecessor's tail (see pdl_wait in the kernel)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  VDA_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, d));
   VDA_CUDA(cudaGetLastError());
   return 0;
 }

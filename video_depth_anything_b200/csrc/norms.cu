@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ in, T* __restrict__ out, const float* __restrict__ w,
                  const float* __restrict__ b, float eps, long long rows, int C, int drop_group,
                  const float* __restrict__ pe, int pe_rows_per_frame, int pe_frames) {
+  pdl_trigger();   // a PDL-launched successor (GEMM) may be scheduled as this grid drains
   const int lane = threadIdx.x & 31;
   // rows are visited last-to-first: the producer (a GEMM epilogue walking the row tiles upwards) wrote the highest
   // rows last, so they are still in the 126 MB L2, and the consumer GEMM starts at row 0, which this kernel writes last
