@@ -126,6 +126,17 @@ int vda_preprocess_frames(const uint8_t* frames, const int32_t* idx, float* out,
 int vda_copy_frames(const void* src, const int32_t* src_idx, void* dst, const int32_t* dst_idx, int n,
                     int64_t frame_bytes, void* stream);
 
+/* Sequence evaluation (benchmark/eval/eval.py:67-122 eval_depthcrafter + benchmark/eval/metric.py abs_relative_difference,
+ * rmse_linear, delta1_acc): pred = predicted disparity fp32 [frames,hw]; gt = depth [frames,hw], fp32 or fp64 (gt_f64),
+ * <= 1e-3 or >= max_depth = invalid.  Masked least-squares (scale, shift) of clip(pred,1e-3) to 1/(gt+1e-8) over the whole
+ * sequence, then per-frame masked metrics of clip(1/clip(scale pred + shift,1e-3),1e-3,max_depth), averaged over the frames
+ * with valid pixels.  All arithmetic in double (as the reference).  out: device double[3] = {AbsRel, RMSE, delta1};
+ * scale_shift: device double[2]; scratch: device double[VDA_EVAL_LSQ_PARTIALS*5 + frames*VDA_EVAL_SLABS*4]. */
+#define VDA_EVAL_LSQ_PARTIALS 592
+#define VDA_EVAL_SLABS 64
+int vda_eval_sequence(const float* pred, const void* gt, int gt_f64, int frames, int64_t hw, double max_depth, double* out,
+                      double* scale_shift, double* scratch, void* stream);
+
 /* im2col of the 14x14/14 patch-embed conv (patch_embed.py:66,76): x fp32 [frames,3,H,W] ->
  * A h16 [frames*hp*wp, kpad], column = c*196 + ky*14 + kx, zero padded to kpad. */
 int vda_patch_im2col(const float* x, void* A, int frames, int H, int W, int kpad, int dtype, void* stream);
