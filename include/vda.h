@@ -177,6 +177,16 @@ int vda_add_h16(const void* a, const void* b, void* out, int64_t n, int dtype, v
 int vda_lsq_scale_shift(const float* pred, const float* target, int64_t n, float* scale_shift, double* scratch,
                         void* stream);
 
+/* The whole sequential (scale, shift) recurrence of a video in one cooperative kernel (video_depth.py:216-252): what
+ * WindowAligner does window by window with vda_lsq_scale_shift + vda_affine_clamp_blend on the key frame, for the
+ * multi-GPU driver, which walks the chain once the anchor frames of every rank's windows are gathered
+ * (parallel.py).  anchors: fp32 [n_windows, 3, hw] = raw slots 0, 1, 12 of every window; table: fp32 [n_windows, 2]
+ * <- (scale, shift) per window, (1, 0) for window 0; affine == 0 (metric model,
+ * metric_depth/video_depth_anything/video_depth.py:132): all (1, 0).  scratch: double [8 * VDA_LSQ_MAX_PARTIALS].
+ * Bit-identical to the per-window calls (same thread mapping, accumulation order and solve). */
+int vda_align_chain(const float* anchors, int n_windows, int64_t hw, int affine, float* table, double* scratch,
+                    void* stream);
+
 /* out = max(0, s*x + t) with (s,t) read from device memory; if blend_w != NULL (fp32 [frames]) then
  * out[f] = prev[f]*(1-w[f]) + max(0, s*x[f]+t)*w[f]  (video_depth.py:234-250, utils/util.py:65-74).
  * x, prev, out: fp32 [frames, hw]. */

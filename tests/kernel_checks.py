@@ -264,6 +264,59 @@ def check_attention_spatial(frames, N, heads, dt, seed=0):
     return _err(out, ref), _tol(ref, dt) * 2
 
 
+def check_attention_spatial_growing(frames, N, heads, dt, mode, seed=0):
+    """Inputs that force the online-softmax RESCALE branch (attention_spatial.cu: the TMEM round trip of O when the
+    running row maximum grows by more than 2^8 in log2 units, i.e. by > 44.4 in raw q.k units):
+      ramp     q.k grows linearly along the key index by ~70 per 128-key tile for even query rows and falls for odd
+               rows (one warp holds rows that rescale at every tile next to rows that never do);
+      outlier  moderate logits plus ONE key in the last (partial) key tile whose logit is ~ +200 above the rest;
+      late     the row maximum sits in the last key for every row after a long flat stretch (l must survive the
+               rescale of an accumulated sum).
+    Reference: fp32 SDPA on the same 16-bit inputs."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    q = torch.randn(frames, N, heads, 64, generator=g) * 0.5
+    k = torch.randn(frames, N, heads, 64, generator=g) * 0.5
+    v = torch.randn(frames, N, heads, 64, generator=g)
+    u = torch.ones(64) / 8.0                                   # unit vector
+    pos = torch.linspace(-1.0, 1.0, N).view(1, N, 1, 1)
+    if mode == "ramp":
+        per_tile = 70.0                                        # raw-logit growth per 128 keys (> 44.4)
+        amp = per_tile * N / 128.0 / 2.0                       # q.k = +-8 * amp/8 * pos ...
+        sign = torch.where(torch.arange(N) % 2 == 0, 1.0, -1.0).view(1, N, 1, 1)
+        q = q + sign * 8.0 * u
+        k = k + pos * (amp / 8.0) * u
+    elif mode == "outlier":
+        q = q + 6.0 * u
+        k[:, N - 1] += 36.0 * u                                # q.k ~ +216 for the very last key
+    elif mode == "late":
+        q = q + 6.0 * u
+        k[:, N - 1] += 9.7 * u                               # e^(58/8) ~ N: both parts weigh about the same
+        k[:, : N - 1] *= 0.05                                  # flat stretch: l accumulates ~N before the jump
+    qkv = torch.stack([q, k, v], dim=2).to(DEV).to(dt).contiguous()      # [frames, N, 3, heads, 64]
+    qf, kf, vf = qkv.float().permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(frames, N, heads * 64)
+    out = torch.empty(frames, N, heads * 64, device=DEV, dtype=dt)
+    ops.attention_spatial(qkv, out, frames, N, heads)
+    torch.cuda.synchronize()
+    return _err(out, ref), _tol(ref, dt) * 2
+
+
+def check_groupnorm_offset(frames, hw, C, dt, offset, seed=0):
+    """|mean| >> std (what ReLU'd feature maps of real checkpoints look like): E[x^2] - mean^2 in fp32 would lose
+    the variance; the shifted / Chan-merged statistics must not.  The input is quantised to 16 bit first, the fp32
+    reference sees the same values."""
+    x = (_rand((frames, hw, C), seed, 1.0) + offset).to(dt)
+    w = 1 + _rand((C,), seed + 1, 0.1)
+    b = _rand((C,), seed + 2, 0.1)
+    ref = F.group_norm(x.double().permute(0, 2, 1), 32, w.double(), b.double(), 1e-6).permute(0, 2, 1).float()
+    out = torch.empty_like(x)
+    ops.groupnorm(x, w, b, 1e-6, out, frames, hw)
+    torch.cuda.synchronize()
+    # one output rounding only: statistics errors would show up far above it
+    eps = 2 ** -8 if dt == torch.bfloat16 else 2 ** -11
+    return _err(out, ref), eps * (ref.abs().max().item()) + 1e-5
+
+
 def check_attention_temporal(T, hw, C, dt, seed=0):
     heads = 8
     qkv = _rand((T * hw, 3 * C), seed, 1.0, dt)
@@ -355,6 +408,45 @@ def check_lsq_affine(hw, seed=0):
     return e, 2e-4
 
 
+def check_align_chain(K, h, w, affine=True, seed=0):
+    """The fused (scale, shift) recurrence (one cooperative kernel) against the per-window kernels WindowAligner.push
+    launches (lsq_scale_shift + re-alignment of the key frame): the tables must be BIT-identical (1 GPU and N GPUs
+    produce the same video), and close to the oracle's numpy restatement of utils/util.py:40-62."""
+    import numpy as np
+    from oracle.vda_oracle import compute_scale_and_shift
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(1, 3, h, w, generator=g) + 0.2
+    anchors = (base * (1.0 + 0.3 * torch.rand(K, 1, 1, 1, generator=g)) + 0.2 * torch.randn(K, 3, h, w, generator=g)
+               - 0.1 * torch.arange(K).view(K, 1, 1, 1) / K).to(DEV).contiguous()
+    scratch = torch.zeros(8 * ops.LSQ_MAX_PARTIALS, device=DEV, dtype=torch.float64)
+    table = torch.full((K, 2), -7.0, device=DEV)
+    ops.align_chain(anchors, table, scratch, affine=affine)
+    # per-window path, exactly as WindowAligner.push sequences it
+    ref_t = torch.zeros(K, 2, device=DEV)
+    ref_t[0, 0] = 1.0
+    ss = torch.tensor([1.0, 0.0], device=DEV)
+    ref = torch.stack([anchors[0, 0], anchors[0, 2]])
+    sc2 = torch.zeros(4 * ops.LSQ_MAX_PARTIALS, device=DEV, dtype=torch.float64)
+    for k in range(1, K):
+        if affine:
+            ops.lsq_scale_shift(anchors[k, 0:2], ref, ss, sc2)
+        ref_t[k].copy_(ss)
+        ops.affine_clamp_blend(anchors[k, 2:3], ss, ref[1:2])
+    torch.cuda.synchronize()
+    assert torch.equal(table, ref_t), f"chain table differs from the per-window kernels: {(table - ref_t).abs().max().item():.3e}"
+    # oracle (numpy float32 sums): same recurrence on the host
+    a = anchors.cpu().numpy()
+    r0, r1 = a[0, 0], a[0, 2].copy()
+    e = 0.0
+    for k in range(1, K):
+        s_, t_ = (1.0, 0.0)
+        if affine:
+            s_, t_ = compute_scale_and_shift(np.concatenate([a[k, 0].ravel(), a[k, 1].ravel()]), np.concatenate([r0.ravel(), r1.ravel()]))
+        e = max(e, abs(float(s_) - table[k, 0].item()), abs(float(t_) - table[k, 1].item()))
+        r1 = np.maximum(a[k, 2] * np.float32(table[k, 0].item()) + np.float32(table[k, 1].item()), 0)
+    return e, 2e-4
+
+
 BF, HF = torch.bfloat16, torch.float16
 CHECKS = [
     # --- plain GEMM: tile / tail coverage, epilogues ---
@@ -403,11 +495,32 @@ CHECKS = [
     ("groupnorm 3x100x192 fp16", lambda: check_groupnorm(3, 100, 192, HF)),
     ("groupnorm 3x1369x64 bf16", lambda: check_groupnorm(3, 1369, 64, BF)),
     ("groupnorm 2x50x384 bf16", lambda: check_groupnorm(2, 50, 384, BF)),
+    ("groupnorm 4x361x1024 bf16 mean=50 std", lambda: check_groupnorm_offset(4, 361, 1024, BF, 50.0)),
+    ("groupnorm 2x5476x256 fp16 mean=30 std", lambda: check_groupnorm_offset(2, 5476, 256, HF, 30.0)),
+    ("groupnorm 3x1369x64 fp16 mean=-200 std", lambda: check_groupnorm_offset(3, 1369, 64, HF, -200.0)),
     # --- attention ---
     ("attn spatial 2x1370x16 bf16", lambda: check_attention_spatial(2, 1370, 16, BF)),
     ("attn spatial 3x21x6 fp16", lambda: check_attention_spatial(3, 21, 6, HF)),
     ("attn spatial 1x2443x2 bf16", lambda: check_attention_spatial(1, 2443, 2, BF)),
     ("attn spatial 1x128x1 bf16", lambda: check_attention_spatial(1, 128, 1, BF)),
+    ("attn spatial 4x300x3 bf16 (pair + split item)", lambda: check_attention_spatial(4, 300, 3, BF)),
+    ("attn spatial 2x129x2 fp16 (2 tiles, partial 1)", lambda: check_attention_spatial(2, 129, 2, HF)),
+    ("attn spatial 40x1370x16 bf16 (all CTAs, many items)", lambda: check_attention_spatial(40, 1370, 16, BF)),
+    ("attn spatial 3x257x1 bf16 (split, n_kv=3)", lambda: check_attention_spatial(3, 257, 1, BF)),
+    ("attn spatial 2x1370x6 fp16", lambda: check_attention_spatial(2, 1370, 6, HF)),
+    # forced online-softmax rescale (never taken with unit-normal q/k)
+    ("attn rescale ramp 2x1370x4 bf16", lambda: check_attention_spatial_growing(2, 1370, 4, BF, "ramp")),
+    ("attn rescale ramp 2x1370x4 fp16", lambda: check_attention_spatial_growing(2, 1370, 4, HF, "ramp")),
+    ("attn rescale ramp 1x2443x2 bf16", lambda: check_attention_spatial_growing(1, 2443, 2, BF, "ramp")),
+    ("attn rescale ramp 1x2443x2 fp16", lambda: check_attention_spatial_growing(1, 2443, 2, HF, "ramp")),
+    ("attn rescale ramp 3x129x2 bf16", lambda: check_attention_spatial_growing(3, 129, 2, BF, "ramp")),
+    ("attn rescale ramp 3x129x2 fp16", lambda: check_attention_spatial_growing(3, 129, 2, HF, "ramp")),
+    ("attn rescale outlier 2x1370x4 bf16", lambda: check_attention_spatial_growing(2, 1370, 4, BF, "outlier")),
+    ("attn rescale outlier 2x1370x4 fp16", lambda: check_attention_spatial_growing(2, 1370, 4, HF, "outlier")),
+    ("attn rescale outlier 1x2443x2 bf16", lambda: check_attention_spatial_growing(1, 2443, 2, BF, "outlier")),
+    ("attn rescale outlier 3x129x2 fp16", lambda: check_attention_spatial_growing(3, 129, 2, HF, "outlier")),
+    ("attn rescale late max 2x1370x4 bf16", lambda: check_attention_spatial_growing(2, 1370, 4, BF, "late")),
+    ("attn rescale late max 1x2443x2 fp16", lambda: check_attention_spatial_growing(1, 2443, 2, HF, "late")),
     ("attn temporal 32x50x1024 bf16", lambda: check_attention_temporal(32, 50, 1024, BF)),
     ("attn temporal 32x77x256 fp16", lambda: check_attention_temporal(32, 77, 256, HF)),
     ("attn temporal 8x30x192 bf16", lambda: check_attention_temporal(8, 30, 192, BF)),
@@ -426,12 +539,20 @@ CHECKS = [
     ("bilinear f32 identity", lambda: check_bilinear_f32(2, 56, 70, 56, 70)),
     ("add h16", lambda: check_add(8 * 1000, BF)),
     ("lsq + affine/clamp/blend", lambda: check_lsq_affine(60 * 80)),
+    ("align chain K=12 60x80", lambda: check_align_chain(12, 60, 80)),
+    ("align chain K=94 518x518", lambda: check_align_chain(94, 518, 518)),
+    ("align chain K=5 15x14 (hw % 4 = 2)", lambda: check_align_chain(5, 15, 14)),
+    ("align chain K=7 7x9 (hw odd)", lambda: check_align_chain(7, 7, 9)),
+    ("align chain K=6 30x40 identity (metric)", lambda: check_align_chain(6, 30, 40, affine=False)),
+    ("align chain K=1", lambda: check_align_chain(1, 30, 40)),
 ]
 
 
-def main():
+def main(filters=()):
     bad = 0
     for name, fn in CHECKS:
+        if filters and not any(f in name for f in filters):
+            continue
         try:
             e, tol = fn()
             ok = e <= tol and e == e
@@ -451,4 +572,4 @@ def main():
 if __name__ == "__main__":
     import os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    sys.exit(1 if main() else 0)
+    sys.exit(1 if main(tuple(sys.argv[1:])) else 0)

@@ -123,3 +123,100 @@ def test_frame_spans_tile_the_video():
         for world in (1, 2, 3, 8):
             spans = [frame_span(p[0], p[-1] + 1, K, n) if len(p) else (0, 0) for p in partition_windows(K, world)]
             assert [f for lo, hi in spans for f in range(lo, hi)] == list(range(n)), (n, world, spans)
+
+
+# ------------------------------------------------------------------------------------------------ two-phase driver
+class _CpuKernels:
+    """CPU stand-in for the libvda kernels two_phase_finalise sequences (numpy float32 arithmetic written like the
+    reference's own lines, video_depth.py:227-250): the test exercises the product's exchange + sequencing code."""
+
+    def __init__(self):
+        from video_depth_anything_b200.windows import INTERP_LEN
+        step = 1.0 / (INTERP_LEN - 1)
+        self.w = [0.0] + [i * step for i in range(1, INTERP_LEN - 1)] + [1.0]
+
+    def align_chain(self, anchors, affine):
+        from oracle import vda_oracle as O
+        a = anchors.numpy()
+        K = a.shape[0]
+        table = np.zeros((K, 2), np.float32)
+        table[0] = (1.0, 0.0)
+        ref0, ref1 = a[0, 0], a[0, 2].copy()
+        for k in range(1, K):
+            s, t = (1.0, 0.0)
+            if affine:
+                s, t = O.compute_scale_and_shift(np.concatenate([a[k, 0], a[k, 1]]), np.concatenate([ref0, ref1]))
+            table[k] = (s, t)
+            ref1 = a[k, 2] * np.float32(s) + np.float32(t)
+            ref1[ref1 < 0] = 0
+        return torch.from_numpy(table)
+
+    def affine_clamp_blend(self, x, ss, out, prev=None, blend=False):
+        s, t = np.float32(ss[0].item()), np.float32(ss[1].item())
+        v = x.numpy() * s + t
+        v[v < 0] = 0
+        if blend:
+            p = prev.numpy()
+            v = np.stack([p[i] * (1 - self.w[i]) + v[i] * self.w[i] for i in range(v.shape[0])]).astype(np.float32)
+        out.copy_(torch.from_numpy(v))
+        return out
+
+
+def _two_phase_worker(rank, world, port, n_frames, mode, out_dir):
+    from video_depth_anything_b200.parallel import two_phase_finalise
+    if world > 1:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        K = num_windows(n_frames)
+        parts = partition_windows(K, world)
+        counts = [len(p) for p in parts]
+        # (negative values too: the clamp must act exactly where the reference's does)
+        raws = torch.stack([fake_raw(k) - 0.3 for k in parts[rank]]) if counts[rank] else torch.empty(0, INFER_LEN, 6, 5)
+        got = []
+        two_phase_finalise(raws, counts, K, n_frames, mode == "affine", _CpuKernels(),
+                           lambda fr, f0: got.append((f0, fr.clone().numpy())))
+        np.save(os.path.join(out_dir, f"r{rank}.npy"), np.array(got, dtype=object), allow_pickle=True)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_frames,mode", [(1, 70, "affine"), (2, 70, "affine"), (2, 131, "identity"),
+                                                 (3, 200, "affine"), (3, 100, "affine")])
+def test_two_phase_finalise_matches_sequential_alignment(tmp_path, world, n_frames, mode):
+    """The scalable driver's exchange (halo point-to-point, anchor all-gather) + per-rank finalisation, run with gloo on
+    CPU tensors, emits every video frame exactly once and equals the reference's sequential alignment of the full
+    window stack (oracle restatement of video_depth.py:216-252)."""
+    from oracle import vda_oracle as O
+    if min(len(p) for p in partition_windows(num_windows(n_frames), world)) == 0:
+        pytest.skip("the two-phase form needs a window on every rank (the driver falls back otherwise)")
+    port = _free_port()
+    if world == 1:
+        _two_phase_worker(0, 1, port, n_frames, mode, str(tmp_path))
+    else:
+        mp.spawn(_two_phase_worker, args=(world, port, n_frames, mode, str(tmp_path)), nprocs=world, join=True)
+    K = num_windows(n_frames)
+    full = [(fake_raw(k) - 0.3).numpy() for k in range(K)]
+    ref = O.align_windows([w[i].copy() for w in full for i in range(INFER_LEN)], n_frames, mode)
+    out = np.full_like(ref, np.nan)
+    seen = np.zeros(n_frames, dtype=int)
+    for r in range(world):
+        for f0, fr in np.load(os.path.join(str(tmp_path), f"r{r}.npy"), allow_pickle=True):
+            out[f0:f0 + fr.shape[0]] = fr
+            seen[f0:f0 + fr.shape[0]] += 1
+    assert (seen == 1).all(), seen
+    np.testing.assert_allclose(out, ref, rtol=2e-6, atol=2e-6)
+
+
+def test_rank_core_slices_are_disjoint_and_cover():
+    from video_depth_anything_b200.parallel import rank_core_slice
+    cores = list(range(3, 27))                       # 24 cores, ids not starting at 0
+    for world in (1, 2, 3, 4, 8):
+        sl = [rank_core_slice(r, world, cores) for r in range(world)]
+        flat = [c for s in sl for c in s]
+        assert len(set(flat)) == len(flat) and set(flat) <= set(cores)
+        assert all(len(s) == len(cores) // world for s in sl)
+    assert rank_core_slice(1, 8, list(range(12))) == list(range(12))      # < 2 cores per rank: no pinning
+    with pytest.raises(ValueError):
+        rank_core_slice(2, 2, cores)

@@ -75,14 +75,11 @@ def timing_report(steps):
         return
     buf = (C.c_ulonglong * 24)()
     lib.vda_debug_sa_timing(buf)
-    names = ["wait S", "ld S+max", "o_done+rescale", "exp", "wait token", "st P tail", "epilogue", "loop"]
+    names = ["wait S", "ld S+max", "rescale chk", "exp rest", "exp0+o_done", "st P tail", "epilogue", "loop"]
     for t in range(2):
         tot = sum(buf[t * 8 + k] for k in range(8))
         print(f"  WG{t}: total {tot} cyc, per step {tot / steps:.0f}: " +
               ", ".join(f"{n} {buf[t * 8 + k] / steps:.0f}" for k, n in enumerate(names)))
-    mn = ["wait K(+Q)", "wait s_free A", "wait s_free B", "wait V", "wait p_ready A", "wait p_ready B", "-", "issue"]
-    print("  MMA: per step " + ", ".join(f"{n} {buf[16 + k] / steps:.0f}" for k, n in enumerate(mn)))
-
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "temporal":
@@ -93,7 +90,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "timing":
         run(8, 1370, 16, torch.bfloat16, iters=1, check=False)
         # CTA 0 of 148 handles items 0,148,...: 768 items -> 6 items (5 full + 1 half) -> 66 / 55 steps
-        timing_report(66)
+        timing_report(61)   # (5 pairs x 11 + the split item's 6 / 5 steps)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "prof":      # short run for ncu
         run(8, 1370, 16, torch.bfloat16, iters=2, check=False)

@@ -220,11 +220,7 @@ static int launch_temporal(const void* qkv, void* out, int T_, int hw, int C, in
   while (hpc > 1 && (heads % hpc != 0 || static_cast<size_t>(hpc) * 3 * 32 * DHP * 2 > 48 * 1024)) --hpc;
   const size_t smem = static_cast<size_t>(hpc) * 3 * 32 * DHP * 2;
   auto k = temporal_attention_kernel<T, DHP>;
-  static bool attr = false;
-  if (!attr) {
-    VDA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
-  }
+  VDA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(k), 64 * 1024));   // per (kernel, device)
   dim3 grid(hw, heads / hpc);
   const int threads = 32 * hpc < 128 ? 128 : 32 * hpc;    // >= 4 warps share the load loop
   k<<<grid, threads, smem, st>>>(static_cast<const T*>(qkv), static_cast<T*>(out), T_, hw, C, heads, hpc);

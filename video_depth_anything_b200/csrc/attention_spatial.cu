@@ -2,22 +2,34 @@
 //
 //   out[f, n, h, :] = softmax_n'( q[f,n,h,:] . k[f,n',h,:] / sqrt(64) ) v[f,n',h,:]       d = 64, N ~ 1370..2443
 //
-// Persistent kernel, one CTA (384 threads = 3 warpgroups) per SM; a work item is (frame, head, pair of 128-query
-// tiles); the per-CTA item list is processed as ONE flat stream of key-tile steps (S of the next item's first key
-// tile is issued while the softmax of the current item's last tile runs; Q is double-buffered):
+// Persistent kernel, one CTA (384 threads = 3 warpgroups) per SM.  A CTA runs TWO independent tile streams
+// (t = 0 / 1), each made of one MMA-issuing warp and one softmax warpgroup that owns a 128-query tile:
 //   warp 0      TMA producer: Q tiles once per item, K / V tiles (128 keys x 64) through two 3-slot rings
-//   warp 1      tcgen05.mma issuer + TMEM owner:  S = Q K^T  (SS form, 128 x kv x 64)  and  O += P V  (TS form: P is
-//               read from TMEM, V from smem as an MN-major operand -- no transpose of V anywhere)
-//   warps 2-3   idle (they only donate registers: setmaxnreg.dec on warpgroup 0, .inc on the softmax warpgroups)
-//   warps 4-7   softmax warpgroup of query tile A      \  one thread per query row: the 128 scores of a row are read
-//   warps 8-11  softmax warpgroup of query tile B      /  from TMEM straight into that thread's registers (no shuffles)
-// TMEM (512 columns): S_A | S_B (128 fp32 columns each), O_A | O_B (64), P_A | P_B (64: 128 packed 16-bit keys).
+//   warp 1 / 2  tcgen05.mma issuer of stream 0 / 1:  S = Q K^T  (SS form, 128 x kv x 64)  and  O += P V  (TS form:
+//               P is read from TMEM, V from smem as an MN-major operand -- no transpose of V anywhere).  S of step
+//               j+1 is issued before P V of step j.  One issuer per stream: a stream never waits for the other
+//               stream's softmax (round 1 had one issuer walking S0 S1 PV0 PV1 in a fixed order, which cost each
+//               warpgroup ~500 cycles per step in front of its P store)
+//   warp 3      idle (donates registers: setmaxnreg.dec on warpgroup 0, .inc on the softmax warpgroups)
+//   warps 4-7   softmax warpgroup of stream 0      \  one thread per query row: the 128 scores of a row are read
+//   warps 8-11  softmax warpgroup of stream 1      /  from TMEM straight into that thread's registers (no shuffles)
+// Work items (one flat list per CTA; the K / V rings never drain between items, Q is double-buffered):
+//   PAIR    two neighbouring query tiles of one (frame, head): both streams consume every K / V tile (one L2 -> smem
+//           load serves 2 x 128 queries)
+//   SPLIT   the odd last query tile of a (frame, head) (N = 1370: 11 tiles): ONE query tile whose key tiles are
+//           divided between the streams (stream 0: tiles 0..ja-1, stream 1: ja..n_kv-1, loaded interleaved); the two
+//           partial results (m, l, O) are merged through shared memory by warpgroup 0 (standard split-KV flash merge).
+//           Round 1 ran these items on one stream with the other idle (8 % of the kernel's time)
+//   SINGLE  the same odd tile on stream 0 only (when there is just one key tile, or -DVDA_SA_NO_SPLIT)
+// Every ring slot is seen by BOTH issuers in the same order: the owner of a use issues its MMAs and commits the
+// slot's `empty` barrier, the other one waits for `full` and arrives plainly (count 2), so the phase accounting does
+// not depend on the item kind.
+// TMEM (512 columns): S_0 | S_1 (128 fp32 columns each), O_0 | O_1 (64), P_0 | P_1 (64: 128 packed 16-bit keys).
 // Because a warpgroup copies S to registers before it starts the exponentials, the issuer refills S with the next
-// key tile immediately (s_free); P has its own columns, so S(j+1) never waits for O += P(j) V(j).  The two query
-// tiles share every K/V tile (halves the L2 -> smem traffic) and keep the MUFU busy while the other warpgroup syncs.
+// key tile immediately (s_free); P has its own columns, so S(j+1) never waits for O += P(j) V(j).
 // Online softmax in fp32 with lazy rescaling: O / l are only rescaled when the running row maximum grows by more
 // than 2^8 (rare after the first key tiles), done by the owning warp through a TMEM round trip.
-// The kernel is exp-bound (MUFU.EX2: 16/clk/SM vs 8192 dense FLOP/clk/SM, d = 64), see DESIGN.md.
+// The kernel is bound by the instruction issue of the softmax warps (MUFU.EX2: 16/clk/SM), see DESIGN.md.
 #include "../../include/vda.h"
 #include "common.cuh"
 
@@ -31,10 +43,13 @@ constexpr int KS = 3, VS = 3;      // K / V ring depth
 constexpr int THREADS = 384;
 constexpr int REGS_CTRL = 56, REGS_SOFTMAX = 224;   // setmaxnreg budgets: 128*56 + 256*224 <= 64K
 constexpr uint32_t TILE_BYTES = BM * D * 2;   // 16 KB: one Q, K or V tile
-constexpr uint32_t SMEM_BYTES = (4 + KS + VS) * TILE_BYTES + 1024;   // Q: 2 buffers x 2 tiles
+constexpr uint32_t XCH_FLOATS = (D + 2) * BM; // split-item exchange: O_1 [64][128], m_1 [128], l_1 [128]
+constexpr uint32_t SMEM_BYTES = (4 + KS + VS) * TILE_BYTES + XCH_FLOATS * 4 + 1024;   // Q: 2 buffers x 2 tiles
 // TMEM columns
 constexpr uint32_t COL_S = 0, COL_O = 256, COL_P = 384;
 constexpr float RESCALE_LOG2 = 8.0f;
+enum { PAIR = 0, SPLIT = 1, SINGLE = 2 };
+enum { BAR_XCH_FULL = 1, BAR_XCH_EMPTY = 2 };   // named barriers (0 is __syncthreads)
 }  // namespace sa
 
 struct SaParams {
@@ -43,12 +58,14 @@ struct SaParams {
   int n_pairs;         // full pairs of query tiles per (frame, head)
   int n_items;         // FH * n_pairs + (n_qt odd ? FH : 0)
   int n_kv;            // key tiles
+  int ja;              // split items: stream 0 takes key tiles [0, ja), stream 1 [ja, n_kv)
+  int split;           // odd tiles are SPLIT items (else SINGLE)
   void* out;
 };
 
 struct SaItem {
   int frame, head, q0;   // q0: first query row of tile A
-  bool has_b;
+  int kind;
 };
 
 __device__ __forceinline__ SaItem sa_decode(const SaParams& p, int item) {
@@ -58,16 +75,27 @@ __device__ __forceinline__ SaItem sa_decode(const SaParams& p, int item) {
   if (item < fh_total * p.n_pairs) {
     fh = item / p.n_pairs;
     tile = 2 * (item - fh * p.n_pairs);
-    it.has_b = true;
+    it.kind = sa::PAIR;
   } else {
     fh = item - fh_total * p.n_pairs;
     tile = p.n_qt - 1;
-    it.has_b = false;
+    it.kind = p.split ? sa::SPLIT : sa::SINGLE;
   }
   it.frame = fh / p.heads;
   it.head = fh - it.frame * p.heads;
   it.q0 = tile * sa::BM;
   return it;
+}
+__device__ __forceinline__ int sa_kind(const SaParams& p, int item) {
+  return item < p.frames * p.heads * p.n_pairs ? sa::PAIR : (p.split ? sa::SPLIT : sa::SINGLE);
+}
+// does stream t consume ring use u (the u-th K / V tile loaded for an item of this kind)?
+__device__ __forceinline__ bool sa_mine(int kind, int t, int u) {
+  return kind == sa::PAIR ? true : (kind == sa::SINGLE ? t == 0 : (u & 1) == t);
+}
+// key tile loaded by ring use u
+__device__ __forceinline__ int sa_tile(const SaParams& p, int kind, int u) {
+  return kind == sa::SPLIT ? ((u & 1) ? p.ja + (u >> 1) : (u >> 1)) : u;
 }
 
 __device__ __forceinline__ int sa_kv_cols(const SaParams& p, int j) {   // columns of key tile j, rounded up to 32
@@ -83,24 +111,12 @@ __device__ unsigned long long g_sa_timing[3][8];
 #define SA_T(i) do { } while (0)
 #endif
 
-// Exp-phase hand-over token between the two softmax warpgroups (-DVDA_SA_TOKEN): off by default.  Micro-benchmarks
-// (tools/microbench/exp_phase.cu, mufu_issue.cu) show that a lone warp per scheduler issues one MUFU.EX2 per ~9.7
-// cycles (1315 cycles per 128x128 tile for the kernel's instruction mix) while two warps per scheduler share the
-// dispatch port and need ~2000 cycles for two tiles whatever the MUFU / polynomial split, so exclusive ownership of
-// the MUFU buys nothing any more; letting the warpgroups drift freely measured 0.385 vs 0.396 ms per layer.
-#ifdef VDA_SA_TOKEN
-#define SA_TOKEN(x) x
-#else
-#define SA_TOKEN(x) do { } while (0)
-#endif
-
 // exp2 on the FMA / ALU pipes for a pair of values (Cody-Waite: x = j + f, j = round(x), f in [-0.5, 0.5];
 // 2^f by a degree-3 minimax polynomial, max rel. error 7.7e-5 -- below the 16-bit rounding of P; 2^j by adding j
 // to the exponent field).  A quarter of the exponentials of a score tile take this path so that the MUFU (16 ex2/clk/SM)
 // is no longer the only unit that can produce them.
 #ifndef VDA_SA_POLY_MASK
-#define VDA_SA_POLY_MASK 3     // pair p of a row uses the polynomial when (p & MASK) == MASK; 1: 50%, 3: 25%, 255: none
-                               // (measured per layer: none 0.416 ms, 25% 0.395 ms, 50% 0.445 ms -- issue-slot bound beyond 25%)
+#define VDA_SA_POLY_MASK 3     // pair p of a row uses the polynomial when (p & MASK) == MASK; 1: 50%, 3: 25%, 7: 12.5%, 255: none
 #endif
 __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   x.x = fmaxf(x.x, -126.f);
@@ -137,16 +153,16 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // smem map: Q[buffer 0: A, B | buffer 1: A, B] | K[KS] | V[VS]
-  const uint32_t offQ = 0, offK = 4 * TILE_BYTES, offV = (4 + KS) * TILE_BYTES;
+  // smem map: Q[buffer 0: A, B | buffer 1: A, B] | K[KS] | V[VS] | split-item exchange
+  const uint32_t offQ = 0, offK = 4 * TILE_BYTES, offV = (4 + KS) * TILE_BYTES, offX = (4 + KS + VS) * TILE_BYTES;
   const int n_my = (p.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                    static_cast<int>(gridDim.x);   // items of this CTA: blockIdx.x + i * gridDim.x
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
-    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-    for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
-    for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 2); }
+    for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 2); }
+    for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 2); }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_ready[t], 1);
       mbar_init(&s_free[t], 128);
@@ -172,10 +188,11 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
         const int qb = i & 1;
         uint8_t* sQ = smem_gen + offQ + qb * 2 * TILE_BYTES;
         mbar_wait(&q_empty[qb], ((i >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&q_full[qb], it.has_b ? 2 * TILE_BYTES : TILE_BYTES);
+        mbar_arrive_expect_tx(&q_full[qb], it.kind == PAIR ? 2 * TILE_BYTES : TILE_BYTES);
         tma_load_4d(sQ, &tmQKV, &q_full[qb], 0, it.head, it.q0, it.frame);
-        if (it.has_b) tma_load_4d(sQ + TILE_BYTES, &tmQKV, &q_full[qb], 0, it.head, it.q0 + BM, it.frame);
-        for (int j = 0; j < p.n_kv; ++j) {
+        if (it.kind == PAIR) tma_load_4d(sQ + TILE_BYTES, &tmQKV, &q_full[qb], 0, it.head, it.q0 + BM, it.frame);
+        for (int u = 0; u < p.n_kv; ++u) {
+          const int j = sa_tile(p, it.kind, u);
           mbar_wait(&k_empty[ks], kph ^ 1u);
           mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
           tma_load_4d(smem_gen + offK + ks * TILE_BYTES, &tmQKV, &k_full[ks], 0, p.heads + it.head, j * BN, it.frame);
@@ -187,91 +204,102 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
           if (++vs == VS) { vs = 0; vph ^= 1u; }
         }
       }
-    } else if (warp == 1) {
-      // ===================================== MMA issuer =======================================
+    } else if (warp == 1 || warp == 2) {
+      // ===================================== MMA issuer of stream t ============================
       // The whole warp runs the (warp-uniform) control flow; one elected lane issues the tcgen05 instructions.
+      const int t = warp - 1;
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
-      uint32_t n_s[2] = {0, 0}, n_pv[2] = {0, 0};     // running counts of S / PV tiles issued per query tile
+      uint32_t n_s = 0, n_pv = 0;          // running counts of S / PV tiles issued by this stream
+      int ki = 0, ku = 0, vi = 0, vu = 0;  // cursors over the flat (item, ring use) sequence of the K and V rings
+      int s_item = -1, pv_item = -1;       // item of this stream's latest S / PV (first-use detection)
       const uint32_t idesc_pv = umma_idesc(H16<T>::kUmmaFmt, D) | kIdescBMnMajor;
-      const int n_full = p.frames * p.heads * p.n_pairs;   // items below this index have two query tiles
-#ifdef VDA_SA_TIMING
-      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
-#endif
+      const int stride = static_cast<int>(gridDim.x);
 
-      // S(i, j) for the query tiles of the i-th item of this CTA
-      auto issue_s_step = [&](int i, int j) {
-        const int nt = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) < n_full ? 2 : 1;
-        const int qb = i & 1;
-        SA_T(7);
-        if (j == 0) mbar_wait(&q_full[qb], (i >> 1) & 1u);
-        mbar_wait(&k_full[ks], kph);
-        SA_T(0);
-        const int cols = sa_kv_cols(p, j);
-        const uint32_t idesc = umma_idesc(H16<T>::kUmmaFmt, static_cast<uint32_t>(cols));
-        const uint64_t db = umma_desc_sw128(smem_base + offK + ks * TILE_BYTES);
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(&s_free[t], (n_s[t] & 1u) ^ 1u);    // the warpgroup has copied the previous S to registers
-          tc_fence_after();
-          SA_T(1 + t);
-          const uint64_t da = umma_desc_sw128(smem_base + offQ + (qb * 2 + t) * TILE_BYTES);
-          if (elect_one()) {
+      // Walk the K ring up to and including this stream's next own use and issue its S; uses that belong to the
+      // other stream are acknowledged on the way.  false: the item list is exhausted.
+      auto next_s = [&]() -> bool {
+        while (ki < n_my) {
+          const int kind = sa_kind(p, static_cast<int>(blockIdx.x) + ki * stride);
+          const bool mine = sa_mine(kind, t, ku);
+          const int qb = ki & 1;
+          mbar_wait(&k_full[ks], kph);
+          if (mine) {
+            if (s_item != ki) {                         // first S of the item: its Q tile(s) must have landed
+              mbar_wait(&q_full[qb], (ki >> 1) & 1u);
+              s_item = ki;
+            }
+            const int cols = sa_kv_cols(p, sa_tile(p, kind, ku));
+            const uint32_t idesc = umma_idesc(H16<T>::kUmmaFmt, static_cast<uint32_t>(cols));
+            const uint64_t db = umma_desc_sw128(smem_base + offK + ks * TILE_BYTES);
+            const uint64_t da = umma_desc_sw128(smem_base + offQ + (qb * 2 + (kind == PAIR ? t : 0)) * TILE_BYTES);
+            mbar_wait(&s_free[t], (n_s & 1u) ^ 1u);     // the warpgroup has copied the previous S to registers
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < D / 16; ++k) umma_f16(tmem_base + COL_S + t * BN, da + 2u * k, db + 2u * k, idesc, k);
-            umma_commit(&s_ready[t]);
+              for (int k = 0; k < D / 16; ++k) umma_f16(tmem_base + COL_S + t * BN, da + 2u * k, db + 2u * k, idesc, k);
+              umma_commit(&s_ready[t]);
+              umma_commit(&k_empty[ks]);
+            }
+            ++n_s;
+          } else if (elect_one()) {
+            mbar_arrive(&k_empty[ks]);
+          }
+          if (ku == p.n_kv - 1 && elect_one()) {        // end of the item: this stream is done with its Q buffer
+            if (s_item == ki) umma_commit(&q_empty[qb]);   // ... once its S MMAs have retired
+            else mbar_arrive(&q_empty[qb]);
           }
           __syncwarp();
-          ++n_s[t];
+          if (++ks == KS) { ks = 0; kph ^= 1u; }
+          if (++ku == p.n_kv) { ku = 0; ++ki; }
+          if (mine) return true;
         }
-        if (elect_one()) {
-          umma_commit(&k_empty[ks]);
-          if (j == p.n_kv - 1) umma_commit(&q_empty[qb]);   // last S of the item: Q is free once these retire
-        }
-        __syncwarp();
-        if (++ks == KS) { ks = 0; kph ^= 1u; }
+        return false;
       };
-
-      if (n_my > 0) issue_s_step(0, 0);
-      for (int i = 0; i < n_my; ++i) {
-        const int nt = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) < n_full ? 2 : 1;
-        for (int j = 0; j < p.n_kv; ++j) {
-          // S of the next step of the flat stream (next key tile, or the first key tile of the next item)
-          if (j + 1 < p.n_kv) issue_s_step(i, j + 1);
-          else if (i + 1 < n_my) issue_s_step(i + 1, 0);
-          // O += P(j) V(j)
-          const int nk = sa_kv_cols(p, j) >> 4;
-          SA_T(7);
+      // Same walk over the V ring: O += P V of this stream's next own use.
+      auto next_pv = [&]() -> bool {
+        while (vi < n_my) {
+          const int kind = sa_kind(p, static_cast<int>(blockIdx.x) + vi * stride);
+          const bool mine = sa_mine(kind, t, vu);
           mbar_wait(&v_full[vs], vph);
-          SA_T(3);
-          const uint64_t db = umma_desc_sw128_mn(smem_base + offV + vs * TILE_BYTES);
-          for (int t = 0; t < nt; ++t) {
-            mbar_wait(&p_ready[t], n_pv[t] & 1u);
+          if (mine) {
+            const int nk = sa_kv_cols(p, sa_tile(p, kind, vu)) >> 4;
+            const uint64_t db = umma_desc_sw128_mn(smem_base + offV + vs * TILE_BYTES);
+            const uint32_t acc0 = pv_item == vi ? 1u : 0u;   // first P V of an item overwrites O
+            pv_item = vi;
+            mbar_wait(&p_ready[t], n_pv & 1u);
             tc_fence_after();
-            SA_T(4 + t);
             if (elect_one()) {
               for (int k = 0; k < nk; ++k)   // 16 keys per MMA: 8 TMEM columns of P, 16 rows (2048 B) of V
                 umma_f16_ts(tmem_base + COL_O + t * D, tmem_base + COL_P + t * (BN / 2) + 8u * k, db + 128u * k,
-                            idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                            idesc_pv, (acc0 | static_cast<uint32_t>(k)) != 0u ? 1u : 0u);
               umma_commit(&o_done[t]);
+              umma_commit(&v_empty[vs]);
             }
-            __syncwarp();
-            ++n_pv[t];
+            ++n_pv;
+          } else if (elect_one()) {
+            mbar_arrive(&v_empty[vs]);
           }
-          if (elect_one()) umma_commit(&v_empty[vs]);
           __syncwarp();
           if (++vs == VS) { vs = 0; vph ^= 1u; }
+          if (++vu == p.n_kv) { vu = 0; ++vi; }
+          if (mine) return true;
         }
+        return false;
+      };
+
+      bool have = next_s();
+      while (have) {
+        const bool nxt = next_s();   // S of the next step of the flat stream (next key tile, or the next item's first)
+        next_pv();                   // O += P V of the current step
+        have = nxt;
       }
-#ifdef VDA_SA_TIMING
-      SA_T(7);
-      if (blockIdx.x == 0 && lane == 0)
-        for (int k = 0; k < 8; ++k) g_sa_timing[2][k] = static_cast<unsigned long long>(tacc[k]);
-#endif
+      next_pv();                     // acknowledge the other stream's trailing V uses (K uses: done by the last next_s)
     }
   } else {
     // ===================================== softmax warpgroups ===============================
     reg_inc<REGS_SOFTMAX>();
-    const int t = (warp - 4) >> 2;                    // query tile handled by this warpgroup
+    const int t = (warp - 4) >> 2;                    // stream / query tile handled by this warpgroup
     const int quad = warp & 3;                        // TMEM lane quadrant of this warp
     const int row = quad * 32 + lane;                 // query row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
@@ -280,30 +308,22 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
     const uint32_t tP = tmem_base + lane_base + COL_P + t * (BN / 2);
     const float sc = 0.125f * 1.4426950408889634f;    // d^-0.5 * log2(e)
     const float2 sc2 = make_float2(sc, sc);
-    uint32_t cnt = 0;                                 // running key-tile counter of this query tile
+    uint32_t cnt = 0;                                 // running key-tile counter of this stream
     T* outp = reinterpret_cast<T*>(p.out);
+    float* xch = reinterpret_cast<float*>(smem_gen + offX);
 #ifdef VDA_SA_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #endif
 
-    // The exponentials are MUFU-bound and one warp per scheduler saturates the MUFU, so the two warpgroups take
-    // turns: a token (named barriers 1 / 2) is handed over after each exp phase, and a warpgroup runs everything
-    // else of its step (S load, row max, TMEM stores, barriers) while the other one owns the MUFU.
-    const int tok_mine = 1 + t, tok_other = 2 - t;
-    (void)tok_mine; (void)tok_other;
-    if (t == 1) SA_TOKEN(named_bar_arrive(tok_other, 256));     // warpgroup A owns the first exp phase
-
     for (int i = 0; i < n_my; ++i) {
       const SaItem it = sa_decode(p, blockIdx.x + i * gridDim.x);
-      if (t == 1 && !it.has_b) {                      // single-tile item: just pass the token along
-        for (int j = 0; j < p.n_kv; ++j) {
-          SA_TOKEN(named_bar_sync(tok_mine, 256));
-          if (i + 1 < n_my || j + 1 < p.n_kv) SA_TOKEN(named_bar_arrive(tok_other, 256));   // (B's very last hand-over has no taker)
-        }
-        continue;
-      }
+      // key tiles of this stream: PAIR all, SPLIT [0, ja) / [ja, n_kv), SINGLE all / none
+      const int j_begin = (it.kind == SPLIT && t == 1) ? p.ja : 0;
+      const int j_end = it.kind == SPLIT ? (t == 0 ? p.ja : p.n_kv) : ((it.kind == SINGLE && t == 1) ? 0 : p.n_kv);
+      if (j_begin >= j_end) continue;
       float m_run = 0.f, l_run = 0.f;
-      for (int j = 0; j < p.n_kv; ++j, ++cnt) {
+      for (int j = j_begin; j < j_end; ++j, ++cnt) {
+        const bool first = j == j_begin;
         const int cols = sa_kv_cols(p, j);
         const int valid = p.N - j * BN;
         uint32_t s[BN];
@@ -356,17 +376,20 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
         }
         SA_T(1);
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        if (j > 0) {   // O += P(j-1) V(j-1) was issued a whole exp phase ago: P and O are ours again
-          mbar_wait(&o_done[t], (cnt - 1u) & 1u);
-          tc_fence_after();
-        }
-        if (j == 0) {
+        // O += P(j-1) V(j-1) was issued by this stream's own issuer as soon as P(j-1) was complete; P and O are ours
+        // again once it has retired.  Normally that wait is taken as late as possible (in front of the first P store,
+        // behind the first 32 exponentials); only a rescale needs O earlier.
+        bool pv_done = first;
+        if (first) {
           m_run = mx;
         } else {
           const float m_new = fmaxf(m_run, mx);
           const bool need = (m_new - m_run) * sc > RESCALE_LOG2;
           if (__any_sync(0xffffffffu, need)) {
             // rare: rescale O (TMEM round trip by the owning warp)
+            mbar_wait(&o_done[t], (cnt - 1u) & 1u);
+            tc_fence_after();
+            pv_done = true;
             float alpha = 1.f;
             if (need) {
               alpha = exp2f((m_run - m_new) * sc);
@@ -386,14 +409,11 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
           }
         }
         SA_T(2);
-        // ---- exp phase (owns the MUFU): P = exp2(s*sc - m*sc), row sum, pack to 16 bit, store to TMEM ----
-        SA_TOKEN(named_bar_sync(tok_mine, 256));
-        SA_T(4);
+        // ---- exp phase: P = exp2(s*sc - m*sc), row sum, pack to 16 bit, store to TMEM ----
         const float nmb = -m_run * sc;
         const float2 nmb2 = make_float2(nmb, nmb);
         float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
-        auto exp_chunk = [&](int c) {
-          uint32_t pk[16];
+        auto exp_chunk = [&](int c, uint32_t (&pk)[16]) {
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
             float2 x0 = __ffma2_rn(make_float2(__uint_as_float(s[c + k]), __uint_as_float(s[c + k + 1])), sc2, nmb2);
@@ -408,16 +428,34 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
             pk[k >> 1] = H16<T>::pack2(x0.x, x0.y);
             pk[(k >> 1) + 1] = H16<T>::pack2(x1.x, x1.y);
           }
-          tmem_st16(tP + (c >> 1), pk);
         };
+        {
+          uint32_t pk[16];
+          exp_chunk(0, pk);                    // cols >= 32 always (N >= 1)
+          if (!pv_done) {
+            mbar_wait(&o_done[t], (cnt - 1u) & 1u);
+            tc_fence_after();
+          }
+          tmem_st16(tP, pk);
+        }
+        SA_T(4);
         if (cols == BN) {   // straight-line code for full key tiles: the scheduler hides the FMAs behind the MUFU
-          exp_chunk(0); exp_chunk(32); exp_chunk(64); exp_chunk(96);
+#pragma unroll
+          for (int c = 32; c < BN; c += 32) {
+            uint32_t pk[16];
+            exp_chunk(c, pk);
+            tmem_st16(tP + (c >> 1), pk);
+          }
         } else {
 #pragma unroll
-          for (int c = 0; c < BN; c += 32)
-            if (c < cols) exp_chunk(c);
+          for (int c = 32; c < BN; c += 32) {
+            if (c < cols) {
+              uint32_t pk[16];
+              exp_chunk(c, pk);
+              tmem_st16(tP + (c >> 1), pk);
+            }
+          }
         }
-        if (t == 0 || i + 1 < n_my || j + 1 < p.n_kv) SA_TOKEN(named_bar_arrive(tok_other, 256));
         SA_T(3);
         l_run += (la.x + la.y) + (lb.x + lb.y);
         tmem_st_wait();
@@ -428,28 +466,67 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
       // ---- epilogue: O / l -> 16 bit -> global ----
       mbar_wait(&o_done[t], (cnt - 1u) & 1u);
       tc_fence_after();
-      const float inv = 1.f / l_run;
-      const int q = it.q0 + t * BM + row;
-      T* orow = outp + (static_cast<long long>(it.frame) * p.N + q) * (static_cast<long long>(p.heads) * D) +
-                it.head * D;
+      if (it.kind == SPLIT && t == 1) {
+        // hand (O_1, m_1, l_1) to warpgroup 0 through shared memory ([value][row]: conflict-free)
+        if (i > 0 && sa_kind(p, static_cast<int>(blockIdx.x) + (i - 1) * static_cast<int>(gridDim.x)) == SPLIT)
+          named_bar_sync(BAR_XCH_EMPTY, 256);         // warpgroup 0 has consumed the previous hand-over
 #pragma unroll
-      for (int c = 0; c < D; c += 32) {
-        uint32_t o[32];
-        tmem_ld32(tO + c, o);
-        tmem_ld_wait();
-        if (q < p.N) {
+        for (int c = 0; c < D; c += 32) {
+          uint32_t o[32];
+          tmem_ld32(tO + c, o);
+          tmem_ld_wait32(o);
 #pragma unroll
-          for (int k = 0; k < 32; k += 8) {
-            uint4 u;
-            u.x = H16<T>::pack2(__uint_as_float(o[k]) * inv, __uint_as_float(o[k + 1]) * inv);
-            u.y = H16<T>::pack2(__uint_as_float(o[k + 2]) * inv, __uint_as_float(o[k + 3]) * inv);
-            u.z = H16<T>::pack2(__uint_as_float(o[k + 4]) * inv, __uint_as_float(o[k + 5]) * inv);
-            u.w = H16<T>::pack2(__uint_as_float(o[k + 6]) * inv, __uint_as_float(o[k + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + c + k) = u;
+          for (int k = 0; k < 32; ++k) xch[(c + k) * BM + row] = __uint_as_float(o[k]);
+        }
+        xch[D * BM + row] = m_run;
+        xch[(D + 1) * BM + row] = l_run;
+        tc_fence_before();   // the O reads above are ordered before this thread's next p_ready arrive
+        named_bar_arrive(BAR_XCH_FULL, 256);
+      } else {
+        float fa = 1.f, fb = 0.f;
+        if (it.kind == SPLIT) {
+          // merge the two halves of the key range:  O = (O_0 2^(m_0-m) + O_1 2^(m_1-m)) / (l_0 2^(m_0-m) + l_1 2^(m_1-m))
+          named_bar_sync(BAR_XCH_FULL, 256);
+          const float mb = xch[D * BM + row], lbv = xch[(D + 1) * BM + row];
+          const float m = fmaxf(m_run, mb);
+          fa = exp2f((m_run - m) * sc);
+          fb = exp2f((mb - m) * sc);
+          const float inv = 1.f / (l_run * fa + lbv * fb);
+          fa *= inv;
+          fb *= inv;
+        } else {
+          fa = 1.f / l_run;
+        }
+        const int q = it.q0 + (it.kind == PAIR ? t * BM : 0) + row;
+        T* orow = outp + (static_cast<long long>(it.frame) * p.N + q) * (static_cast<long long>(p.heads) * D) +
+                  it.head * D;
+#pragma unroll
+        for (int c = 0; c < D; c += 32) {
+          uint32_t o[32];
+          tmem_ld32(tO + c, o);
+          tmem_ld_wait32(o);
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(o[k]) * fa;
+          if (it.kind == SPLIT) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = fmaf(xch[(c + k) * BM + row], fb, v[k]);
+          }
+          if (q < p.N) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              uint4 u;
+              u.x = H16<T>::pack2(v[k], v[k + 1]);
+              u.y = H16<T>::pack2(v[k + 2], v[k + 3]);
+              u.z = H16<T>::pack2(v[k + 4], v[k + 5]);
+              u.w = H16<T>::pack2(v[k + 6], v[k + 7]);
+              *reinterpret_cast<uint4*>(orow + c + k) = u;
+            }
           }
         }
+        tc_fence_before();   // the O reads above are ordered before this thread's next p_ready arrive
+        if (it.kind == SPLIT && i + 1 < n_my) named_bar_arrive(BAR_XCH_EMPTY, 256);   // (split items are the tail of the list)
       }
-      tc_fence_before();   // the O reads above are ordered before this thread's next p_ready arrive
       SA_T(6);
     }
 #ifdef VDA_SA_TIMING
@@ -499,24 +576,22 @@ extern "C" int vda_attention_spatial(const void* qkv, void* out, int frames, int
   p.n_pairs = p.n_qt / 2;
   p.n_items = frames * heads * p.n_pairs + ((p.n_qt & 1) ? frames * heads : 0);
   p.n_kv = (N + sa::BN - 1) / sa::BN;
+  p.ja = (p.n_kv + 1) / 2;
+#ifdef VDA_SA_NO_SPLIT
+  p.split = 0;
+#else
+  p.split = p.n_kv >= 2 ? 1 : 0;
+#endif
   p.out = out;
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == VDA_BF16) {
     auto k = spatial_attention_tc_kernel<__nv_bfloat16>;
-    static bool attr = false;
-    if (!attr) {
-      VDA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sa::SMEM_BYTES));
-      attr = true;
-    }
+    VDA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(k), sa::SMEM_BYTES));
     k<<<grid, sa::THREADS, sa::SMEM_BYTES, st>>>(tm, p);
   } else {
     auto k = spatial_attention_tc_kernel<__half>;
-    static bool attr = false;
-    if (!attr) {
-      VDA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sa::SMEM_BYTES));
-      attr = true;
-    }
+    VDA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(k), sa::SMEM_BYTES));
     k<<<grid, sa::THREADS, sa::SMEM_BYTES, st>>>(tm, p);
   }
   VDA_CUDA(cudaGetLastError());

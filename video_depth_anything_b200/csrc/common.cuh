@@ -402,7 +402,12 @@ constexpr uint32_t kIdescBMnMajor = 1u << 16;   // instruction-descriptor bit: B
 // host helpers shared by the TMA-fed kernels (defined in gemm.cu)
 int make_tensor_map(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims,
                     const cuuint64_t* strides_bytes, const cuuint32_t* box);
-int sm_count();
+int sm_count();        // SM count of the CURRENT device (cached per device)
+int current_device();  // cudaGetDevice, -1 on error
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: the opt-in is cached per
+// (kernel, device), so a second GPU in the same process gets its own cudaFuncSetAttribute call (defined in gemm.cu).
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);
 
 // ---------------------------------------------------------------------------------------------
 // misc

@@ -3,18 +3,19 @@
 //
 //   out[M,N] = A[M,K] . Wt[N,K]^T      A, Wt: bf16|fp16, K-major;  fp32 accumulators in TMEM
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
-//   warp 0     : TMA producer (one lane)   smem ring of `stages` x {A 128x64, B block_n x 64}, SWIZZLE_128B
-//   warp 1     : TMEM allocator + tcgen05.mma issuer (one lane), UMMA 128 x block_n x 16
-//   warps 2..5 : epilogue; tcgen05.ld of the 128-lane accumulator (one row per thread), fused math,
-//                vectorised global stores.  Two accumulator stages in TMEM overlap the epilogue of
-//                tile i with the MMAs of tile i+1.
+// One persistent CTA per SM (or one CTA pair per TPC, cta_group::2), 320 threads, warp-specialised:
+//   warp 0     : TMA producer (one elected lane)   smem ring of `stages` x {A 128x64, B rows x 64}, SWIZZLE_128B
+//   warp 1     : TMEM allocator + tcgen05.mma issuer (one elected lane), UMMA 128|256 x block_n x 16
+//   warps 2..9 : epilogue, two warps per TMEM lane quadrant (each drains half of the tile's columns): tcgen05.ld,
+//                fused math, staged through a swizzled smem tile so that every global access is a row segment.
+//                Two accumulator stages in TMEM overlap the epilogue of tile i with the MMAs of tile i+1.
 // block_n (16..256, multiple of 16) is a run-time parameter: it only appears in the instruction
 // descriptor, the B tensor map and loop bounds.
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <mutex>
+#include <unordered_map>
 
 #include "../../include/vda.h"
 #include "common.cuh"
@@ -747,15 +748,36 @@ int make_tensor_map(CUtensorMap* m, int dtype, const void* base, int rank, const
   return 0;
 }
 
-static int g_sm_count = 0;
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return dev;
+}
+
+// per-device caches: a process may drive several GPUs (one engine per device)
+constexpr int kMaxDevices = 64;
 int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
-  return g_sm_count;
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (dev >= 0 && dev < kMaxDevices && cached[dev] > 0) return cached[dev];
+  int n = 0;
+  if (dev < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev >= 0 && dev < kMaxDevices) cached[dev] = n;
+  return n;
+}
+
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> opted[kMaxDevices];   // largest opt-in so far per (device, kernel)
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices)
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = opted[dev].find(kernel);
+  if (it != opted[dev].end() && it->second >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e == cudaSuccess) opted[dev][kernel] = bytes;
+  return e;
 }
 
 static int pick_block_n(int N, int tiles_m) {
@@ -775,11 +797,7 @@ static int pick_block_n(int N, int tiles_m) {
 template <typename T, int EPI, bool CONV, bool STAGED, int SPEC, bool CTA2>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, size_t smem, cudaStream_t st) {
   auto kfn = gemm_kernel<T, EPI, CONV, STAGED, SPEC, CTA2>;
-  static size_t attr_smem = 0;   // per instantiation: largest dynamic smem opted in so far
-  if (smem > attr_smem) {
-    VDA_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_smem = smem;
-  }
+  VDA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kfn), smem));   // per (kernel, device)
   const bool pdl = pdl_enabled();
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kThreads);

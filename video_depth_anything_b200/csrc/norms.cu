@@ -1,5 +1,5 @@
 // Bandwidth-bound normalisation kernels: LayerNorm (warp per row, fp32 statistics, 128-bit accesses) and
-// GroupNorm over NHWC activations (per-slab partial sums, fixed-order reduction, then apply; no atomics).
+// GroupNorm over NHWC activations (per-slab shifted (mean, M2) partials, fixed-order Chan merge, then apply; no atomics).
 #include "../../include/vda.h"
 #include "common.cuh"
 
@@ -81,9 +81,13 @@ layernorm_kernel(const void* __restrict__ in, T* __restrict__ out, const float* 
 
 // ---------------------------------------------------------------------------------------------
 // GroupNorm over [frames, hw, C] (NHWC).  Pass 1: every CTA reduces a slab of pixels of one frame to per-group
-// (sum, sumsq) partials; pass 1b sums the slabs of a frame in a fixed order (no atomics anywhere: results are
-// bit-reproducible run to run); pass 2: normalise + affine.
-// stats layout: partials [frames][slabs][groups][2], then totals [frames][groups][2].
+// (mean, M2 = sum of squared deviations) partials; pass 1b merges the slabs of a frame in a fixed order with Chan's
+// parallel-variance update (no atomics anywhere: results are bit-reproducible run to run); pass 2: normalise + affine.
+// The slab sums are taken of d = x - K_g with K_g = the group's first channel at the slab's first pixel, so that
+// M2 = sum d^2 - (sum d)^2 / n cancels against (mean - K_g)^2 ~ var instead of mean^2: a group whose |mean| is far
+// above its standard deviation (ReLU'd activations of real checkpoints) keeps its variance (round 1 used
+// E[x^2] - mean^2 in fp32).
+// stats layout: partials [frames][slabs][groups][2] = (mean, M2), then totals [frames][groups][2] = (mean, var).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -99,6 +103,11 @@ groupnorm_stats_kernel(const T* __restrict__ in, float* __restrict__ partials, i
   const int vecs = C >> 3;
   const long long total = static_cast<long long>(p1 - p0) * vecs;
   const T* base = in + (static_cast<long long>(frame) * hw + p0) * C;
+  // shift of each of this thread's channel pairs: first channel of the pair's group at the slab's first pixel
+  const int c0t = (threadIdx.x % vecs) * 8;
+  float kk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) kk[i] = H16<T>::to_f(base[((c0t + 2 * i) / cpg) * cpg]);
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const uint4 u = *reinterpret_cast<const uint4*>(base + idx * 8);
@@ -106,8 +115,9 @@ groupnorm_stats_kernel(const T* __restrict__ in, float* __restrict__ partials, i
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 f = H16<T>::unpack2(wds[i]);
-      s[i] += f.x + f.y;
-      q[i] += f.x * f.x + f.y * f.y;
+      const float dx = f.x - kk[i], dy = f.y - kk[i];
+      s[i] += dx + dy;
+      q[i] += dx * dx + dy * dy;
     }
   }
 #pragma unroll
@@ -115,7 +125,7 @@ groupnorm_stats_kernel(const T* __restrict__ in, float* __restrict__ partials, i
   __syncthreads();
   if (threadIdx.x < groups) {
     // thread g sums, in thread order, every channel pair that belongs to group g (cpg is even: a pair never
-    // straddles groups)
+    // straddles groups; all of them were shifted by the same K_g)
     const int g = threadIdx.x;
     float ts = 0.f, tq = 0.f;
     for (int t = 0; t < static_cast<int>(blockDim.x); ++t) {
@@ -124,24 +134,32 @@ groupnorm_stats_kernel(const T* __restrict__ in, float* __restrict__ partials, i
       for (int i = 0; i < 4; ++i)
         if ((c0 + 2 * i) / cpg == g) { ts += sh_s[t][i]; tq += sh_q[t][i]; }
     }
+    const float n = static_cast<float>(p1 - p0) * cpg;
+    const float kg = H16<T>::to_f(base[g * cpg]);
+    const float md = ts / n;                              // mean of d
     float* dst = partials + ((static_cast<size_t>(frame) * gridDim.x + blockIdx.x) * groups + g) * 2;
-    dst[0] = ts;
-    dst[1] = tq;
+    dst[0] = kg + md;
+    dst[1] = fmaxf(tq - ts * md, 0.f);
   }
 }
 
 __global__ void groupnorm_reduce_kernel(const float* __restrict__ partials, float* __restrict__ totals, int slabs,
-                                        int groups) {
+                                        int groups, int hw, int pix_per_cta, int cpg) {
   const int frame = blockIdx.x, g = threadIdx.x;
   if (g >= groups) return;
-  float ts = 0.f, tq = 0.f;
+  // Chan et al.: merge (n, mean, M2) of the slabs in slab order
+  float n = 0.f, mean = 0.f, m2 = 0.f;
   for (int sl = 0; sl < slabs; ++sl) {
     const float* src = partials + ((static_cast<size_t>(frame) * slabs + sl) * groups + g) * 2;
-    ts += src[0];
-    tq += src[1];
+    const float nb = static_cast<float>(min(pix_per_cta, hw - sl * pix_per_cta)) * cpg;
+    const float delta = src[0] - mean;
+    const float nn = n + nb;
+    mean += delta * (nb / nn);
+    m2 += src[1] + delta * delta * (n * nb / nn);
+    n = nn;
   }
-  totals[(frame * groups + g) * 2] = ts;
-  totals[(frame * groups + g) * 2 + 1] = tq;
+  totals[(frame * groups + g) * 2] = mean;
+  totals[(frame * groups + g) * 2 + 1] = m2 / n;
 }
 
 template <typename T>
@@ -152,7 +170,6 @@ groupnorm_apply_kernel(const T* __restrict__ in, T* __restrict__ out, const floa
   const int vecs = C >> 3;
   const long long total = static_cast<long long>(frames) * hw * vecs;
   const int cpg = C / groups;
-  const float inv_n = 1.f / (static_cast<float>(hw) * cpg);
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int vcol = static_cast<int>(idx % vecs);
@@ -165,9 +182,7 @@ groupnorm_apply_kernel(const T* __restrict__ in, T* __restrict__ out, const floa
     for (int i = 0; i < 4; ++i) {
       const int c = c0 + 2 * i;
       const int g = c / cpg;     // cpg is even, so both channels of the pair share a group
-      const float s = stats[(frame * groups + g) * 2], q = stats[(frame * groups + g) * 2 + 1];
-      const float mean = s * inv_n;
-      const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+      const float mean = stats[(frame * groups + g) * 2], var = stats[(frame * groups + g) * 2 + 1];
       const float rstd = rsqrtf(var + eps);
       const float2 f = H16<T>::unpack2(wds[i]);
       res[i] = H16<T>::pack2((f.x - mean) * rstd * w[c] + b[c], (f.y - mean) * rstd * w[c + 1] + b[c + 1]);
@@ -223,12 +238,12 @@ extern "C" int vda_groupnorm(const void* in, void* out, const float* w, const fl
   if (g2 > 148u * 16u) g2 = 148u * 16u;
   if (dtype == VDA_BF16) {
     groupnorm_stats_kernel<__nv_bfloat16><<<grid, sthreads, 0, st>>>(static_cast<const __nv_bfloat16*>(in), stats, hw, C, groups, pix_per_cta);
-    groupnorm_reduce_kernel<<<frames, 64, 0, st>>>(stats, totals, slabs, groups);
+    groupnorm_reduce_kernel<<<frames, 64, 0, st>>>(stats, totals, slabs, groups, hw, pix_per_cta, C / groups);
     groupnorm_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out),
                                                               totals, w, b, eps, frames, hw, C, groups);
   } else {
     groupnorm_stats_kernel<__half><<<grid, sthreads, 0, st>>>(static_cast<const __half*>(in), stats, hw, C, groups, pix_per_cta);
-    groupnorm_reduce_kernel<<<frames, 64, 0, st>>>(stats, totals, slabs, groups);
+    groupnorm_reduce_kernel<<<frames, 64, 0, st>>>(stats, totals, slabs, groups, hw, pix_per_cta, C / groups);
     groupnorm_apply_kernel<__half><<<g2, 256, 0, st>>>(static_cast<const __half*>(in), static_cast<__half*>(out), totals, w, b,
                                                        eps, frames, hw, C, groups);
   }

@@ -270,11 +270,7 @@ extern "C" int vda_tail_fused(const void* in, const void* w, const float* bias, 
 #define TAIL_LAUNCH(TT, CCV)                                                                              \
   do {                                                                                                    \
     auto k = tail_fused_kernel<TT, CCV>;                                                                  \
-    static bool attr = false;                                                                             \
-    if (!attr) {                                                                                          \
-      VDA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-      attr = true;                                                                                        \
-    }                                                                                                     \
+    VDA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(k), smem));   /* per (kernel, device) */     \
     k<<<grid, tl::THREADS, smem, st>>>(tm, p);                                                            \
   } while (0)
   if (dtype == VDA_BF16) {

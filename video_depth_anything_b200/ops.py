@@ -253,6 +253,19 @@ def lsq_scale_shift(pred: torch.Tensor, target: torch.Tensor, scale_shift: torch
     _count(2)
 
 
+def align_chain(anchors: torch.Tensor, table: torch.Tensor, scratch: torch.Tensor, affine: bool = True):
+    """(scale, shift) of every window from the gathered anchor frames: anchors fp32 [K,3,h,w] (raw slots 0, 1, 12) ->
+    table fp32 [K,2]; one cooperative kernel, bit-identical to WindowAligner's per-window recurrence."""
+    lib = _lib.load()
+    K = anchors.shape[0]
+    assert anchors.is_contiguous() and anchors.dtype == torch.float32 and anchors.shape[1] == 3
+    assert table.is_contiguous() and table.dtype == torch.float32 and table.numel() == 2 * K
+    assert scratch.dtype == torch.float64 and scratch.numel() >= 8 * LSQ_MAX_PARTIALS
+    check(lib.vda_align_chain(_p(anchors), K, anchors[0, 0].numel(), int(bool(affine)), _p(table), _p(scratch), _stream()))
+    _count()
+    return table
+
+
 def affine_clamp_blend(x: torch.Tensor, scale_shift: torch.Tensor, out: torch.Tensor, prev=None, blend_w=None):
     lib = _lib.load()
     frames = x.shape[0]
@@ -281,6 +294,6 @@ def _profiled(fn, name):
 
 
 for _n in ("preprocess_frames", "copy_frames", "gemm", "layernorm", "groupnorm", "attention_spatial", "attention_temporal", "patch_im2col", "write_cls",
-           "pos_embed_bicubic", "im2col3x3_s2", "bilinear_nhwc", "tail_fused", "bilinear_f32", "add_h16", "lsq_scale_shift",
+           "pos_embed_bicubic", "im2col3x3_s2", "bilinear_nhwc", "tail_fused", "bilinear_f32", "add_h16", "lsq_scale_shift", "align_chain",
            "affine_clamp_blend"):
     globals()[_n] = _profiled(globals()[_n], _n)

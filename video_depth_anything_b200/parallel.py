@@ -105,24 +105,152 @@ def frame_span(k0: int, k1: int, n_windows: int, n_frames: int):
     return min(lo, n_frames), min(hi, n_frames)
 
 
+_PINNED_CORES = [False]
+
+
+def rank_core_slice(rank: int, world: int, cores: Sequence[int]) -> List[int]:
+    """Disjoint, contiguous share of `cores` for local rank `rank` of `world` (pure function; tested on CPU).  Every
+    rank of one host runs a launching thread, a drain thread, two copy threads and a page-touch thread: on a 24-core
+    box with 8 ranks their 40+ runnable threads otherwise migrate over each other's cores and the window phase of
+    every rank slows down (round 1: +100 ms of 500)."""
+    cores = sorted(cores)
+    if world <= 0 or rank < 0 or rank >= world:
+        raise ValueError("bad rank / world")
+    per = len(cores) // world
+    if per < 2:                       # not enough cores to give every rank two: leave the scheduler alone
+        return list(cores)
+    return cores[rank * per:(rank + 1) * per]
+
+
+def _pin_cores(rank: int, world: int) -> None:
+    """Pin this process (all its threads, present and future) to its rank's core slice; once per process, Linux only,
+    VDA_PIN_CORES=0 disables."""
+    if _PINNED_CORES[0] or os.environ.get("VDA_PIN_CORES", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return
+    _PINNED_CORES[0] = True
+    try:
+        mine = rank_core_slice(rank, world, sorted(os.sched_getaffinity(0)))
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, min(torch.get_num_threads(), len(mine))))
+    except OSError:
+        pass
+
+
+_SAME_HOST: dict = {}
+
+
 def _same_host(group) -> bool:
-    import socket
-    names = [None] * dist.get_world_size(group)
-    dist.all_gather_object(names, socket.gethostname(), group=group)
-    return len(set(names)) == 1
+    """All ranks of the group on one host? (one object all-gather per process group, then cached)"""
+    key = id(group)
+    if key not in _SAME_HOST:
+        import socket
+        names = [None] * dist.get_world_size(group)
+        dist.all_gather_object(names, socket.gethostname(), group=group)
+        _SAME_HOST[key] = len(set(names)) == 1
+    return _SAME_HOST[key]
+
+
+class _DeviceKernels:
+    """The libvda kernels two_phase_finalise sequences (tests substitute a CPU stand-in with the same methods)."""
+
+    def __init__(self, dev):
+        from . import ops
+        from .video_depth import make_blend_weights
+        self.ops, self.dev = ops, dev
+        self.blend_w = make_blend_weights(dev)
+
+    def align_chain(self, anchors, affine):
+        table = torch.empty(anchors.shape[0], 2, dtype=torch.float32, device=self.dev)
+        scratch = torch.zeros(8 * self.ops.LSQ_MAX_PARTIALS, dtype=torch.float64, device=self.dev)
+        return self.ops.align_chain(anchors, table, scratch, affine=affine)
+
+    def affine_clamp_blend(self, x, ss, out, prev=None, blend=False):
+        return self.ops.affine_clamp_blend(x, ss, out, prev=prev, blend_w=self.blend_w if blend else None)
+
+
+def two_phase_finalise(raws: torch.Tensor, counts: Sequence[int], K: int, n: int, affine: bool, kern, emit, group=None,
+                       stamp=lambda name: None) -> None:
+    """Steps 1-4 of the two-phase driver for this rank's raw window stack `raws` [counts[rank],32,H,W] (windows
+    partition_windows(K, world)[rank]); see _infer_two_phase.  `kern` supplies align_chain / affine_clamp_blend (libvda
+    on the GPU), `emit(frames [m,H,W], first_video_frame)` receives every finished run of frames exactly once.
+    Pure sequencing + torch.distributed: runs on CPU tensors with gloo too (tests/test_parallel_cpu.py)."""
+    rank, world = _world(group)
+    h0, w0 = raws.shape[-2:]
+    dev = raws.device
+    parts = partition_windows(K, world)
+    k0, k1 = (parts[rank][0], parts[rank][-1] + 1) if counts[rank] else (0, 0)
+    # ---- 1. halo: raw slots 24..31 of the window before my first one (no dependency on the table) ----
+    reqs, halo = [], None
+    owners = [r for r in range(world) if counts[r]]
+    if counts[rank] and world > 1:
+        i = owners.index(rank)
+        if i + 1 < len(owners):
+            reqs.append(dist.P2POp(dist.isend, raws[-1, INFER_LEN - INTERP_LEN:].contiguous(), owners[i + 1], group))
+        if i > 0:
+            halo = torch.empty(INTERP_LEN, h0, w0, dtype=torch.float32, device=dev)
+            reqs.append(dist.P2POp(dist.irecv, halo, owners[i - 1], group))
+    works = dist.batch_isend_irecv(reqs) if reqs else []
+    # ---- 2. anchors (slots 0, 1, 12) of every window on every rank ----
+    kmax = max(counts)
+    mine = torch.zeros(kmax, 3, h0, w0, dtype=torch.float32, device=dev)
+    if counts[rank]:
+        mine[:counts[rank]].copy_(raws[:, [0, 1, KEYFRAME_REF]])
+    if world > 1:
+        flat = torch.empty(world * kmax, 3, h0, w0, dtype=torch.float32, device=dev)   # (concatenated form: gloo too)
+        dist.all_gather_into_tensor(flat, mine, group=group)
+        gathered = flat.view(world, kmax, 3, h0, w0)
+    else:
+        gathered = mine.unsqueeze(0)
+    if all(c == kmax for c in counts):
+        anchors = gathered.view(world * kmax, 3, h0, w0)
+    else:
+        anchors = torch.cat([gathered[r, :counts[r]] for r in range(world)])                  # [K,3,h0,w0]
+    # ---- 3. (scale, shift) of every window: the whole recurrence in one cooperative kernel ----
+    table = kern.align_chain(anchors, affine)                                                  # video_depth.py:227-250
+    stamp("scale/shift table")
+    for w in works:
+        w.wait()
+    # ---- 4. my frames: same kernel sequence as WindowAligner.push with the tabulated (scale, shift), in place in
+    #      the raw stack (the kernels are elementwise): window j's slots 2..9 are cross-faded with the aligned slots
+    #      24..31 of window j-1, slots 10..31 are aligned; its slots [2, 24) are then final video frames
+    #      22k+2 .. 22k+23 and leave at once (the last window keeps its slots 24..31 too) ----
+    for j in range(k1 - k0):
+        k, d = k0 + j, raws[j]
+        if k == 0:                                                   # window 0 is copied unclamped (:222-225)
+            first = 0
+        else:
+            ssk = table[k]
+            if j > 0:
+                prev = raws[j - 1, INFER_LEN - INTERP_LEN:]          # already aligned in place
+            elif k == 1:
+                prev = halo                                          # window 0's frames: never scaled or clamped
+            else:
+                prev = kern.affine_clamp_blend(halo, table[k - 1], halo)
+            head = d[OVERLAP - INTERP_LEN:OVERLAP]
+            kern.affine_clamp_blend(head, ssk, head, prev=prev, blend=True)                        # :234-239
+            kern.affine_clamp_blend(d[OVERLAP:], ssk, d[OVERLAP:])                                 # :241-244
+            first = OVERLAP - INTERP_LEN
+        last = INFER_LEN if k == K - 1 else INFER_LEN - INTERP_LEN
+        f0 = STEP * k + first
+        f1 = min(STEP * k + last, n)
+        if f1 > f0:
+            emit(d[first:first + f1 - f0], f0)
+    stamp("frames blended")
 
 
 @torch.no_grad()
 def _infer_two_phase(model, frames, target_fps, input_size, device, group):
-    """Scalable form for one node (SURVEY.md §8e option 2).  Every rank computes its block of windows; the three
-    anchor frames of every window (slots 0, 1, 12) are all-gathered and every rank runs the tiny sequential
-    scale/shift recurrence itself (same kernels, same order as WindowAligner.push, so the result is bit-identical);
-    then each rank clamps / cross-fades ITS frames (one 8-frame halo from the left neighbour) and downloads them
-    into a POSIX shared-memory array owned by rank 0 -- PCIe, host copies and page faults are spread over all
-    ranks instead of funnelled through one."""
+    """Scalable form for one node (SURVEY.md §8e option 2), the default.  Every rank computes its block of windows
+    with no data-path collective; then
+      1. the last 8 raw slots of every block travel to the next rank (cross-fade halo; NCCL batch_isend_irecv),
+      2. the three anchor frames of every window (slots 0, 1, 12) are all-gathered (NCCL over NVLink, 3.2 MB / window),
+      3. every rank walks the sequential (scale, shift) recurrence itself in ONE cooperative kernel
+         (ops.align_chain: bit-identical to WindowAligner.push's per-window kernels),
+      4. each rank clamps / cross-fades ITS frames in place and downloads them into a POSIX shared-memory array owned
+         by rank 0 -- PCIe, host copies and page faults are spread over all ranks instead of funnelled through one.
+    The result is bit-identical to the single-GPU `infer_video_depth`."""
     from multiprocessing import resource_tracker, shared_memory
-    from . import ops
-    from .video_depth import HostDrain, make_blend_weights
+    from .video_depth import HostDrain
     rank, world = _world(group)
     dev = torch.device(device)
     n, h0, w0 = frames.shape[:3]
@@ -131,6 +259,7 @@ def _infer_two_phase(model, frames, target_fps, input_size, device, group):
     counts = [len(p) for p in parts]
     k0, k1 = (parts[rank][0], parts[rank][-1] + 1) if counts[rank] else (0, 0)
     lo, hi = frame_span(k0, k1, K, n)
+    _pin_cores(rank, world)
     # shared result array: created by rank 0, attached by the others, first-touched per slice in the background
     nbytes = n * h0 * w0 * 4
     box = [None]
@@ -152,70 +281,12 @@ def _infer_two_phase(model, frames, target_fps, input_size, device, group):
 
     with torch.cuda.device(dev):
         stamp("shm ready")
-        drain = HostDrain(host, dev, touch=slice(lo, hi))
+        # one drain per rank on the same host: 2 copy threads and 1 low-priority page-touch thread each
+        drain = HostDrain(host, dev, touch=slice(lo, hi), copy_threads=2, touch_threads=1)
         raws = model.infer_video_depth(frames, target_fps, input_size=input_size, device=dev,
                                        window_ids=list(parts[rank]), raw_only=True)          # [k_r,32,h0,w0]
         stamp("windows computed")
-        # ---- anchors -> (scale, shift) of every window, on every rank ----
-        kmax = max(counts)
-        mine = torch.zeros(kmax, 3, h0, w0, dtype=torch.float32, device=dev)
-        if counts[rank]:
-            mine[:counts[rank]].copy_(raws[:, [0, 1, KEYFRAME_REF]])
-        gathered = torch.empty(world, kmax, 3, h0, w0, dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(gathered, mine, group=group)
-        anchors = torch.cat([gathered[r, :counts[r]] for r in range(world)])                  # [K,3,h0,w0]
-        table = torch.empty(K, 2, dtype=torch.float32, device=dev)
-        ss = torch.tensor([1.0, 0.0], dtype=torch.float32, device=dev)
-        table[0].copy_(ss)
-        scratch = torch.zeros(4 * ops.LSQ_MAX_PARTIALS, dtype=torch.float64, device=dev)
-        ref = torch.stack([anchors[0, 0], anchors[0, 2]])
-        for k in range(1, K):
-            if not model.metric:
-                ops.lsq_scale_shift(anchors[k, 0:2], ref, ss, scratch)                        # video_depth.py:227-232
-            table[k].copy_(ss)
-            ops.affine_clamp_blend(anchors[k, 2:3], ss, ref[1:2])                             # :246-250
-        stamp("scale/shift table")
-        # ---- halo: raw slots 24..31 of the window before my first one ----
-        reqs, halo = [], None
-        owners = [r for r in range(world) if counts[r]]
-        if counts[rank]:
-            i = owners.index(rank)
-            if i + 1 < len(owners):
-                reqs.append(dist.P2POp(dist.isend, raws[-1, INFER_LEN - INTERP_LEN:].contiguous(), owners[i + 1], group))
-            if i > 0:
-                halo = torch.empty(INTERP_LEN, h0, w0, dtype=torch.float32, device=dev)
-                reqs.append(dist.P2POp(dist.irecv, halo, owners[i - 1], group))
-        if reqs:
-            for w in dist.batch_isend_irecv(reqs):
-                w.wait()
-        # ---- my frames: same kernel sequence as WindowAligner.push with the tabulated (scale, shift), in place in the
-        #      raw stack (the kernels are elementwise): window j's slots 2..9 are cross-faded with the aligned slots
-        #      24..31 of window j-1, slots 10..31 are aligned; its slots [2, 24) are then final video frames
-        #      22k+2 .. 22k+23 and go to the host at once (the last window keeps its slots 24..31 too) ----
-        if counts[rank]:
-            blend_w = make_blend_weights(dev)
-            for j in range(k1 - k0):
-                k, d = k0 + j, raws[j]
-                if k == 0:                                                   # window 0 is copied unclamped (:222-225)
-                    first = 0
-                else:
-                    ssk = table[k]
-                    if j > 0:
-                        prev = raws[j - 1, INFER_LEN - INTERP_LEN:]          # already aligned in place
-                    elif k == 1:
-                        prev = halo                                          # window 0's frames: never scaled or clamped
-                    else:
-                        prev = ops.affine_clamp_blend(halo, table[k - 1], halo)
-                    head = d[OVERLAP - INTERP_LEN:OVERLAP]
-                    ops.affine_clamp_blend(head, ssk, head, prev=prev, blend_w=blend_w)            # :234-239
-                    ops.affine_clamp_blend(d[OVERLAP:], ssk, d[OVERLAP:])                          # :241-244
-                    first = OVERLAP - INTERP_LEN
-                last = INFER_LEN if k == K - 1 else INFER_LEN - INTERP_LEN
-                f0 = STEP * k + first
-                f1 = min(STEP * k + last, n)
-                if f1 > f0:
-                    drain.send(d[first:first + f1 - f0], f0)
-            stamp("frames blended")
+        two_phase_finalise(raws, counts, K, n, not model.metric, _DeviceKernels(dev), drain.send, group, stamp)
         drain.finish()
         stamp("downloaded")
     dist.barrier(group=group)
@@ -252,12 +323,11 @@ def infer_video_depth_sharded(model, frames: np.ndarray, target_fps, input_size:
     n, h0, w0 = frames.shape[:3]
     parts = partition_windows(num_windows(n), world)
     counts = [len(p) for p in parts]
-    # Default: the streaming form.  Measured on 2048 x 518 x 518 frames: 2 GPUs 2.10 s either way; 8 GPUs 0.64 s
-    # streaming vs 0.75 s two-phase -- rank 0 downloads its own block while it computes and pulls the other 1.9 GB in
-    # ~70 ms, while the two-phase form ran its window phase ~100 ms slower with 8 ranks (48 page-touching / copy
-    # threads on the box's 24 cores next to the launch threads) for the same ~70 ms tail.  The two-phase form
-    # (VDA_SHARD_MODE=two_phase) is kept for larger frames / longer videos, where rank 0's PCIe link becomes the limit.
-    mode = os.environ.get("VDA_SHARD_MODE", "stream")
+    # Default on one host: the two-phase form (every rank downloads its own frames; the (scale, shift) chain is one
+    # cooperative kernel).  Round 1 defaulted to the streaming form below: rank 0 pulled the other ranks' raw stacks
+    # (unbatched point-to-point) and funnelled all N frames through its one PCIe link -- 70 ms of a 650 ms call at 8
+    # GPUs.  VDA_SHARD_MODE=stream selects it again; it is also the form for ranks spread over several hosts.
+    mode = os.environ.get("VDA_SHARD_MODE", "two_phase")
     if dst == 0 and min(counts) > 0 and mode == "two_phase" and _same_host(group):
         return _infer_two_phase(model, frames, target_fps, input_size, device, group)
     if dst == 0:
@@ -312,5 +382,5 @@ def infer_video_depth_sharded(model, frames: np.ndarray, target_fps, input_size:
         return aligner.result(), target_fps
 
 
-__all__ = ["partition_windows", "gather_window_depths", "stream_window_depths", "frame_span", "infer_video_depth_sharded",
-           "INFER_LEN"]
+__all__ = ["two_phase_finalise", "partition_windows", "gather_window_depths", "stream_window_depths", "frame_span", "rank_core_slice",
+           "infer_video_depth_sharded", "INFER_LEN"]

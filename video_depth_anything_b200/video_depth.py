@@ -10,6 +10,7 @@ buffers while the windows compute.
 """
 from __future__ import annotations
 
+import os
 import queue
 import threading
 from collections import OrderedDict
@@ -25,6 +26,9 @@ from .engine import Engine
 from .synth import ENCODER_DIMS, synth_state_dict
 from .windows import (INFER_LEN, INTERP_LEN, KEYFRAMES, OVERLAP, get_resize_hw, plan_feature_cache,
                       window_source_indices)
+
+
+VALIDATION_DTYPE = torch.float16     # operand type of the `fp32=True` path (see _ensure_engine)
 
 
 class VideoDepthAnything(nn.Module):
@@ -47,6 +51,7 @@ class VideoDepthAnything(nn.Module):
         # parameters live in a plain fp32 state dict with the reference's key set; the engine owns packed copies
         self._sd = synth_state_dict(encoder, features, self.out_channels, num_frames, seed=0)
         self._engine: Optional[Engine] = None
+        self._engine_val: Optional[Engine] = None        # fp32=True (validation precision), built on first use
         self._device = torch.device("cpu")
 
     # ---- nn.Module surface -------------------------------------------------------------------
@@ -63,13 +68,17 @@ class VideoDepthAnything(nn.Module):
         for k in self._sd:
             if k in sd:
                 self._sd[k] = sd[k].detach().to("cpu", torch.float32).clone()
-        if self._engine is not None:
-            self._engine.load(self._sd)
+        for eng in (self._engine, self._engine_val):
+            if eng is not None:
+                eng.load(self._sd)
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     def to(self, device=None, *a, **k):
         if device is not None and not isinstance(device, torch.dtype):
-            self._device = torch.device(device)
+            dev = torch.device(device)
+            if dev.type == "cuda" and dev.index is None:     # 'cuda' and 'cuda:<current>' are the same engine
+                dev = torch.device("cuda", torch.cuda.current_device())
+            self._device = dev
             if self._device.type == "cuda":
                 self._ensure_engine()
         return self
@@ -77,10 +86,22 @@ class VideoDepthAnything(nn.Module):
     def cuda(self, device=None):
         return self.to("cuda" if device is None else device)
 
-    def _ensure_engine(self) -> Engine:
+    def _ensure_engine(self, validation: bool = False) -> Engine:
+        """The engine of the model's dtype; `validation=True`: the high-precision engine behind `fp32=True` (fp16
+        operands -- 11 mantissa bits instead of bf16's 8 -- with fp32 accumulation, residual streams, statistics and
+        softmax; built lazily, holds its own packed copy of the weights)."""
         if self._device.type != "cuda":
             raise RuntimeError("VideoDepthAnything (B200 engine) has no CPU path: call .to('cuda') first")
-        if self._engine is None:
+        if validation and self.dtype != VALIDATION_DTYPE:
+            if self._engine_val is None or self._engine_val.device != self._device:
+                from . import _lib
+                _lib.load()
+                with torch.cuda.device(self._device):
+                    self._engine_val = Engine(self.encoder, self.features, self.out_channels, VALIDATION_DTYPE,
+                                              self._device, self.num_frames)
+                    self._engine_val.load(self._sd)
+            return self._engine_val
+        if self._engine is None or self._engine.device != self._device:
             from . import _lib
             _lib.load()                                  # raises if libvda.so is missing
             with torch.cuda.device(self._device):
@@ -91,9 +112,9 @@ class VideoDepthAnything(nn.Module):
 
     # ---- forward -----------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, stages=None) -> torch.Tensor:
-        """x [B,T,3,H,W] -> depth [B,T,H,W] fp32, >= 0 (video_depth.py:89-164)."""
-        eng = self._ensure_engine()
+    def forward(self, x: torch.Tensor, stages=None, fp32: bool = False) -> torch.Tensor:
+        """x [B,T,3,H,W] -> depth [B,T,H,W] fp32, >= 0 (video_depth.py:89-164).  `fp32=True`: validation precision."""
+        eng = self._ensure_engine(validation=bool(fp32))
         with torch.cuda.device(self._device):
             return eng.forward(x.to(self._device), stages)
 
@@ -108,8 +129,10 @@ class VideoDepthAnything(nn.Module):
         INTER_CUBIC resize + normalisation (one kernel), forward (CUDA-graph replay), output resize, key-frame
         least squares, clamp and cross-fade.  Frames are uploaded in chunks through pinned staging buffers while
         earlier windows compute, finished depth frames stream back the same way; the host never touches a pixel.
-        `fp32` is accepted for signature compatibility; operand precision is the engine's dtype (bf16/fp16
-        tensor-core operands, fp32 accumulation / residual / statistics).
+        `fp32=True` (the reference disables autocast, video_depth.py:203-205 / benchmark/infer/infer.py:58) selects the
+        validation-precision engine: fp16 tensor-core operands with fp32 accumulation, residual streams, statistics and
+        softmax (<= 1e-3 of the fp32 reference on the full ViT-L window, tests/test_forward_gpu.py), whatever the
+        model's own dtype; there is no fp32-operand tensor path on this engine, and the flag is not silently ignored.
         `window_ids` / `raw_only` are the multi-GPU hooks (parallel.py): compute only those windows and return
         the raw, resized per-window depths [len(window_ids),32,H0,W0] on the device, skipping alignment; with
         `aligner` the windows are pushed into that WindowAligner instead (the caller finishes it) and None is returned.
@@ -122,7 +145,7 @@ class VideoDepthAnything(nn.Module):
         if frames.ndim != 4 or frames.shape[3] != 3 or frames.dtype != np.uint8:
             raise ValueError("frames must be uint8 [N,H0,W0,3]")
         self.to(device)
-        eng = self._ensure_engine()
+        eng = self._ensure_engine(validation=bool(fp32))
         n = frames.shape[0]
         h0, w0 = frames.shape[1:3]
         nh, nw = get_resize_hw(h0, w0, input_size)
@@ -158,6 +181,7 @@ class VideoDepthAnything(nn.Module):
                     raws[j].copy_(d)
                 if not raw_only:
                     aligner.push(d)
+            up.close()
             if raw_only:
                 return raws
             if not own_aligner:
@@ -209,6 +233,34 @@ class FeatureCache:
         return eng.head_frames(head_in, INFER_LEN, self.hp, self.wp)
 
 
+_PINNED: dict = {}
+_PINNED_LOCK = threading.Lock()
+
+
+def _pinned_acquire(key, count: int, shape, dtype):
+    """Pinned host staging buffers, cached across calls (cudaHostAlloc of a few hundred MB costs tens of ms and
+    synchronises the device; a serving loop calls infer_video_depth once per video).  One cached set per (purpose,
+    frame size); a caller that finds the set taken by another live object (concurrent calls from several threads)
+    gets a private allocation.  Returns (buffers, token); hand the token back with _pinned_release."""
+    with _PINNED_LOCK:
+        ent = _PINNED.get(key)
+        if ent is not None and not ent["busy"] and len(ent["bufs"]) >= count and tuple(ent["bufs"][0].shape) == tuple(shape):
+            ent["busy"] = True
+            return ent["bufs"][:count], key
+        if ent is not None and ent["busy"]:
+            return [torch.empty(*shape, dtype=dtype).pin_memory() for _ in range(count)], None
+        bufs = [torch.empty(*shape, dtype=dtype).pin_memory() for _ in range(count)]
+        _PINNED[key] = {"bufs": bufs, "busy": True}
+        return bufs, key
+
+
+def _pinned_release(token) -> None:
+    if token is not None:
+        with _PINNED_LOCK:
+            if token in _PINNED:
+                _PINNED[token]["busy"] = False
+
+
 class FrameUploader:
     """Chunked, asynchronous H2D of the uint8 frames a rank needs (pinned double buffer, copy stream); windows wait
     only for the chunks that hold their frames, so the upload overlaps the compute of earlier windows."""
@@ -220,9 +272,14 @@ class FrameUploader:
         self.slot = {i: j for j, i in enumerate(needed)}
         h0, w0 = frames.shape[1:3]
         self.dev = torch.empty(len(needed), h0, w0, 3, dtype=torch.uint8, device=device)
-        self.stage = [torch.empty(self.CHUNK, h0, w0, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.stage, self._stage_token = _pinned_acquire(("upload", h0, w0), 2, (self.CHUNK, h0, w0, 3), torch.uint8)
         self.stage_free = [None, None]           # event: staging buffer consumed by its H2D copy
         self.stream = torch.cuda.Stream(device=device)
+        # `dev` comes from the caching allocator of the compute stream and may be a block that kernels of an earlier call
+        # (still queued on that stream: the raw_only / aligner paths return without synchronising) are yet to read: the
+        # copy stream starts after everything issued so far, and the block is not recycled before the copies are done
+        self.stream.wait_stream(torch.cuda.current_stream(device))
+        self.dev.record_stream(self.stream)
         self.uploaded = 0                        # number of `needed` entries issued so far
         self.chunk_no = 0
 
@@ -252,6 +309,14 @@ class FrameUploader:
         if last_ev is not None:
             torch.cuda.current_stream().wait_event(last_ev)
 
+    def close(self) -> None:
+        """All uploads have been issued: give the staging buffers back once their H2D copies are done."""
+        for ev in self.stage_free:
+            if ev is not None:
+                ev.synchronize()
+        _pinned_release(self._stage_token)
+        self._stage_token = None
+
 
 class HostDrain:
     """Device -> host streaming of finished fp32 frames: D2H into pinned staging buffers on a copy stream, and a drain
@@ -263,10 +328,17 @@ class HostDrain:
     STAGES = 4
     COPY_THREADS = 6
 
-    def __init__(self, host: np.ndarray, device, touch: Optional[slice] = None):
+    def __init__(self, host: np.ndarray, device, touch: Optional[slice] = None, copy_threads: Optional[int] = None,
+                 touch_threads: Optional[int] = None):
+        """`copy_threads` / `touch_threads`: host threads of the drain copies / of the background first-touch (default
+        6 / 6 for a single process; the sharded driver runs one HostDrain per rank on the same host and asks for 2 / 1,
+        see parallel.py)."""
         self.host, self.device = host, device
+        self.COPY_THREADS = copy_threads or self.COPY_THREADS
+        touch_threads = touch_threads or self.COPY_THREADS
         h0, w0 = host.shape[1:]
-        self.stage = [torch.empty(INFER_LEN, h0, w0, dtype=torch.float32).pin_memory() for _ in range(self.STAGES)]
+        self.stage, self._stage_token = _pinned_acquire(("drain", h0, w0), self.STAGES, (INFER_LEN, h0, w0),
+                                                        torch.float32)
         self.stage_free = [threading.Event() for _ in range(self.STAGES)]
         for e in self.stage_free:
             e.set()
@@ -276,9 +348,17 @@ class HostDrain:
         self.error = None
         self.pool = ThreadPoolExecutor(self.COPY_THREADS)
         flat = (host if touch is None else host[touch]).reshape(-1)
-        cuts = np.linspace(0, flat.size, self.COPY_THREADS + 1).astype(np.int64)
-        for i in range(self.COPY_THREADS):
-            self.pool.submit(lambda a=flat[cuts[i]:cuts[i + 1]]: a[::1024].fill(0))
+        cuts = np.linspace(0, flat.size, touch_threads + 1).astype(np.int64)
+        self.touch_pool = ThreadPoolExecutor(touch_threads)
+
+        def first_touch(a):
+            try:     # background work: stay out of the way of the launching thread (Linux: per-thread nice value)
+                os.setpriority(os.PRIO_PROCESS, threading.get_native_id(), 10)
+            except (OSError, AttributeError):
+                pass
+            a[::1024].fill(0)
+
+        self.touch = [self.touch_pool.submit(first_touch, flat[cuts[i]:cuts[i + 1]]) for i in range(touch_threads)]
         self.drainer = threading.Thread(target=self._drain_loop, daemon=True)
         self.drainer.start()
 
@@ -291,6 +371,10 @@ class HostDrain:
             ev, b, lo, hi = job
             try:
                 ev.synchronize()
+                if self.touch:                   # a late page-touch write would zero a float of a drained frame
+                    for f in self.touch:
+                        f.result()
+                    self.touch = []
                 src = self.stage[b].numpy()
                 cuts = np.linspace(0, hi - lo, self.COPY_THREADS + 1).astype(int)
                 list(self.pool.map(lambda i: np.copyto(self.host[lo + cuts[i]:lo + cuts[i + 1]], src[cuts[i]:cuts[i + 1]]),
@@ -323,6 +407,9 @@ class HostDrain:
         self.jobs.join()
         self.drainer.join()
         self.pool.shutdown()
+        self.touch_pool.shutdown()
+        _pinned_release(self._stage_token)       # every drain copy out of the staging buffers has completed
+        self._stage_token = None
         if self.error is not None:
             raise self.error
         return self.host
