@@ -551,7 +551,9 @@ CHECKS = [
 def main(filters=()):
     bad = 0
     for name, fn in CHECKS:
-        if filters and not any(f in name for f in filters):
+        inc = [f for f in filters if not f.startswith("-")]
+        exc = [f[1:] for f in filters if f.startswith("-")]
+        if (inc and not any(f in name for f in inc)) or any(f in name for f in exc):
             continue
         try:
             e, tol = fn()

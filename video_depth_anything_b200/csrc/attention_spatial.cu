@@ -21,9 +21,12 @@
 //           partial results (m, l, O) are merged through shared memory by warpgroup 0 (standard split-KV flash merge).
 //           Round 1 ran these items on one stream with the other idle (8 % of the kernel's time)
 //   SINGLE  the same odd tile on stream 0 only (when there is just one key tile, or -DVDA_SA_NO_SPLIT)
-// Every ring slot is seen by BOTH issuers in the same order: the owner of a use issues its MMAs and commits the
-// slot's `empty` barrier, the other one waits for `full` and arrives plainly (count 2), so the phase accounting does
-// not depend on the item kind.
+// Every `empty` barrier (K / V slots, Q buffers) expects TWO arrivals per use: one tcgen05.commit from each stream that
+// consumes the use; for a use only one stream consumes, the PRODUCER arrives in place of the other stream right after
+// issuing the load.  A stream therefore never waits on, or acknowledges, a slot it does not read -- it only counts
+// it (slot = use index mod ring depth).  (A first version let the non-owner acknowledge the slot when its cursor
+// walked past it; the S look-ahead then waited for tiles the producer could only load after an acknowledgement
+// that sat behind that very wait: a deadlock whenever a stream had two foreign uses in a row.)
 // TMEM (512 columns): S_0 | S_1 (128 fp32 columns each), O_0 | O_1 (64), P_0 | P_1 (64: 128 packed 16-bit keys).
 // Because a warpgroup copies S to registers before it starts the exponentials, the issuer refills S with the next
 // key tile immediately (s_free); P has its own columns, so S(j+1) never waits for O += P(j) V(j).
@@ -191,16 +194,20 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
         mbar_arrive_expect_tx(&q_full[qb], it.kind == PAIR ? 2 * TILE_BYTES : TILE_BYTES);
         tma_load_4d(sQ, &tmQKV, &q_full[qb], 0, it.head, it.q0, it.frame);
         if (it.kind == PAIR) tma_load_4d(sQ + TILE_BYTES, &tmQKV, &q_full[qb], 0, it.head, it.q0 + BM, it.frame);
+        if (it.kind == SINGLE) mbar_arrive(&q_empty[qb]);          // stream 1 never reads this Q buffer
         for (int u = 0; u < p.n_kv; ++u) {
           const int j = sa_tile(p, it.kind, u);
+          const bool both = it.kind == PAIR;                      // else exactly one stream consumes this use
           mbar_wait(&k_empty[ks], kph ^ 1u);
           mbar_arrive_expect_tx(&k_full[ks], TILE_BYTES);
           tma_load_4d(smem_gen + offK + ks * TILE_BYTES, &tmQKV, &k_full[ks], 0, p.heads + it.head, j * BN, it.frame);
+          if (!both) mbar_arrive(&k_empty[ks]);                   // (counts for the phase that has just begun)
           if (++ks == KS) { ks = 0; kph ^= 1u; }
           mbar_wait(&v_empty[vs], vph ^ 1u);
           mbar_arrive_expect_tx(&v_full[vs], TILE_BYTES);
           tma_load_4d(smem_gen + offV + vs * TILE_BYTES, &tmQKV, &v_full[vs], 0, 2 * p.heads + it.head, j * BN,
                       it.frame);
+          if (!both) mbar_arrive(&v_empty[vs]);
           if (++vs == VS) { vs = 0; vph ^= 1u; }
         }
       }
@@ -216,15 +223,15 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
       const uint32_t idesc_pv = umma_idesc(H16<T>::kUmmaFmt, D) | kIdescBMnMajor;
       const int stride = static_cast<int>(gridDim.x);
 
-      // Walk the K ring up to and including this stream's next own use and issue its S; uses that belong to the
-      // other stream are acknowledged on the way.  false: the item list is exhausted.
+      // Advance the K cursor to this stream's next own use and issue its S; uses of the other stream are only counted
+      // (ring slot / phase follow from the use count).  false: the item list is exhausted.
       auto next_s = [&]() -> bool {
         while (ki < n_my) {
           const int kind = sa_kind(p, static_cast<int>(blockIdx.x) + ki * stride);
           const bool mine = sa_mine(kind, t, ku);
           const int qb = ki & 1;
-          mbar_wait(&k_full[ks], kph);
           if (mine) {
+            mbar_wait(&k_full[ks], kph);
             if (s_item != ki) {                         // first S of the item: its Q tile(s) must have landed
               mbar_wait(&q_full[qb], (ki >> 1) & 1u);
               s_item = ki;
@@ -241,15 +248,13 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
               umma_commit(&s_ready[t]);
               umma_commit(&k_empty[ks]);
             }
+            __syncwarp();
             ++n_s;
-          } else if (elect_one()) {
-            mbar_arrive(&k_empty[ks]);
           }
-          if (ku == p.n_kv - 1 && elect_one()) {        // end of the item: this stream is done with its Q buffer
-            if (s_item == ki) umma_commit(&q_empty[qb]);   // ... once its S MMAs have retired
-            else mbar_arrive(&q_empty[qb]);
+          if (ku == p.n_kv - 1 && s_item == ki) {       // end of an item this stream read Q for: release the Q buffer
+            if (elect_one()) umma_commit(&q_empty[qb]); // ... once its S MMAs have retired
+            __syncwarp();
           }
-          __syncwarp();
           if (++ks == KS) { ks = 0; kph ^= 1u; }
           if (++ku == p.n_kv) { ku = 0; ++ki; }
           if (mine) return true;
@@ -261,8 +266,8 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
         while (vi < n_my) {
           const int kind = sa_kind(p, static_cast<int>(blockIdx.x) + vi * stride);
           const bool mine = sa_mine(kind, t, vu);
-          mbar_wait(&v_full[vs], vph);
           if (mine) {
+            mbar_wait(&v_full[vs], vph);
             const int nk = sa_kv_cols(p, sa_tile(p, kind, vu)) >> 4;
             const uint64_t db = umma_desc_sw128_mn(smem_base + offV + vs * TILE_BYTES);
             const uint32_t acc0 = pv_item == vi ? 1u : 0u;   // first P V of an item overwrites O
@@ -276,11 +281,9 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
               umma_commit(&o_done[t]);
               umma_commit(&v_empty[vs]);
             }
+            __syncwarp();
             ++n_pv;
-          } else if (elect_one()) {
-            mbar_arrive(&v_empty[vs]);
           }
-          __syncwarp();
           if (++vs == VS) { vs = 0; vph ^= 1u; }
           if (++vu == p.n_kv) { vu = 0; ++vi; }
           if (mine) return true;
@@ -294,7 +297,6 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
         next_pv();                   // O += P V of the current step
         have = nxt;
       }
-      next_pv();                     // acknowledge the other stream's trailing V uses (K uses: done by the last next_s)
     }
   } else {
     // ===================================== softmax warpgroups ===============================
