@@ -76,6 +76,22 @@ typedef struct vda_gemm_params {
   /* TAIL: N == 32; out is fp32 [rows] */
   const float* tail_w; /* [32] */
   float tail_b;
+
+  /* LayerNorm folding (dinov2_layers/block.py:82-107: x = x + ls1(attn(norm1(x))); x = x + ls2(mlp(norm2(x)))).
+   * Producer (proj / fc2: bias, gamma, fp32 residual updated in place, res1 == out): besides the fp32 rows it writes
+   *   out16          h16 copy of the new rows [rows, ldo]                                  (NULL: not wanted)
+   *   row_stats_out  fp32 [rows, stat_parts, 2] = (mean, M2) of each row over consecutive column groups
+   *                  (layout from vda_gemm_rowstat_layout; stat_parts must match)          (NULL: not wanted)
+   * Consumer (qkv / fc1: bias, optional GELU, h16 out): with row_stats_in != NULL, A holds the UN-normalised h16 rows
+   * and the LayerNorm is applied in the epilogue:  out = rstd_r (acc - mu_r ln_c1[n]) + bias[n],  where Wt holds
+   * h16(ln_weight * W) row-wise, ln_c1[n] = sum_k Wt[n,k] (of the rounded values) and bias[n] = W ln_bias + b;
+   * (mu_r, rstd_r) come from the stat_parts partials of stat_cols columns each (stat_parts * stat_cols == K). */
+  void* out16;
+  float* row_stats_out;
+  const float* row_stats_in;
+  const float* ln_c1;
+  int32_t stat_parts, stat_cols;
+  float ln_eps;
 } vda_gemm_params;
 
 int vda_version(void);
@@ -87,6 +103,8 @@ int vda_device_query(int device, int* sm_count, int* cc_major, int* cc_minor);
  * dinov2_layers/attention.py:44-46, mlp.py:30-32, patch_embed.py:66, dpt.py:60-90,117-124, util/blocks.py:20-32,52-58,
  * 124-126, motion_module/motion_module.py:85,100, motion_module/attention.py:81-83,90,335-338,382-384) */
 int vda_gemm(const vda_gemm_params* p, void* stream);
+/* layout of row_stats_out for an [M, N] output: `parts` partials per row over `part_cols` consecutive columns each */
+int vda_gemm_rowstat_layout(int M, int N, int* parts, int* part_cols);
 
 /* nn.LayerNorm over the last dim (block.py:56,68; dinov2.py:165,309-310; motion_module.py:156-163).
  * in: fp32 (in_f32) or h16 [rows, C]; out: h16 [rows_out, C].
@@ -97,6 +115,12 @@ int vda_gemm(const vda_gemm_params* p, void* stream);
 int vda_layernorm(const void* in, int in_f32, void* out, const float* w, const float* b, float eps, int64_t rows,
                   int C, int dtype, int drop_group, const float* pe, int pe_rows_per_frame, int pe_frames,
                   void* stream);
+
+/* LayerNorm folding, start of the chain (see vda_gemm_params.row_stats_in): h16 copy of the fp32 rows `in` [rows, C]
+ * and their per-row partial statistics fp32 [rows, parts, 2] = (mean, M2) over part_cols consecutive columns each
+ * (parts * part_cols == C), the format a residual GEMM with row_stats_out writes. */
+int vda_rowstats_cast(const float* in, void* out16, float* stats, int64_t rows, int C, int parts, int part_cols, int dtype,
+                      void* stream);
 
 /* GroupNorm(32, C, eps) per frame over an NHWC h16 tensor [frames, hw, C] (motion_module.py:84,110).
  * stats: fp32 scratch of VDA_GN_STATS_FLOATS(frames, groups) floats (per-slab partial sums + per-frame totals;

@@ -36,7 +36,7 @@ def _tol(ref, dt, k=1):
 
 # ------------------------------------------------------------------------------------------------ GEMM
 def check_gemm_plain(M, N, K, dt, bias=True, gamma=False, act=ACT_NONE, res1=None, res2=False, out_f32=False,
-                     out_relu=False, seed=0):
+                     out_relu=False, seed=0, inplace=None):
     a = _rand((M, K), seed, 1.0, dt)
     w = _rand((N, K), seed + 1, 1.0 / math.sqrt(K), dt)
     b = _rand((N,), seed + 2) if bias else None
@@ -60,7 +60,7 @@ def check_gemm_plain(M, N, K, dt, bias=True, gamma=False, act=ACT_NONE, res1=Non
     r2 = _rand((M, N), seed + 5, 1.0, dt) if res2 else None
     if r2 is not None:
         ref = ref + r2.float()
-    inplace = res1 == "f32" and out_f32
+    inplace = (res1 == "f32" and out_f32) if inplace is None else inplace
     out = r1 if inplace else torch.empty(M, N, device=DEV, dtype=torch.float32 if out_f32 else dt)
     orl = torch.empty(M, N, device=DEV, dtype=dt) if out_relu else None
     ops.gemm(a, w, out, bias=b, gamma=g, act=act, res1=r1, res2=r2, out_relu=orl)
@@ -69,6 +69,71 @@ def check_gemm_plain(M, N, K, dt, bias=True, gamma=False, act=ACT_NONE, res1=Non
     if orl is not None:
         e = max(e, _err(orl, F.relu(ref)))
     return e, _tol(ref, dt)
+
+
+def _stats_ref(x, parts):
+    """(mean, M2) of every row over `parts` consecutive column groups, fp64."""
+    M, C = x.shape
+    g = x.double().reshape(M, parts, C // parts)
+    mean = g.mean(-1)
+    return torch.stack([mean, ((g - mean[..., None]) ** 2).sum(-1)], -1)
+
+
+def check_gemm_residual_fold_producer(M, N, K, dt, seed=0, offset=0.0):
+    """proj / fc2 epilogue with the LayerNorm-fold outputs (gemm.cu SPEC 4: residual box in and result box out by TMA):
+    out = (a W^T + b) * gamma + out in place (fp32), out16 = h16(out), row statistics = per-row (mean, M2) over the
+    kernel's column groups.  `offset`: residual rows with |mean| >> std (the shifted sums must keep M2)."""
+    a = _rand((M, K), seed, 1.0, dt)
+    w = _rand((N, K), seed + 1, 1.0 / math.sqrt(K), dt)
+    b = _rand((N,), seed + 2)
+    g = 1.0 + _rand((N,), seed + 3, 0.1)
+    res = _rand((M, N), seed + 4) + offset
+    ref = (a.float() @ w.float().t() + b) * g + res
+    parts, part_cols = ops.rowstat_layout(M, N)
+    assert parts * part_cols == N
+    out = res.clone()
+    o16 = torch.zeros(M, N, device=DEV, dtype=dt)
+    stats = torch.zeros(M, parts, 2, device=DEV)
+    ops.gemm(a, w, out, bias=b, gamma=g, res1=out, out16=o16, row_stats_out=stats)
+    torch.cuda.synchronize()
+    e = _err(out, ref)
+    assert torch.equal(o16, out.to(dt)), "out16 is not the 16-bit rounding of the fp32 rows"
+    sref = _stats_ref(out, parts)
+    e_mean = (stats[..., 0].double() - sref[..., 0]).abs().max().item()
+    rel_m2 = ((stats[..., 1].double() - sref[..., 1]).abs() / (sref[..., 1] + 1e-6)).max().item()
+    assert e_mean < 1e-4 * (1 + abs(offset)) and rel_m2 < 2e-3, f"row statistics off: mean {e_mean:.3e} M2 rel {rel_m2:.3e}"
+    return e, _tol(ref - res, dt) + 1e-6 * (1 + abs(offset))
+
+
+def check_gemm_ln_fold(M, N, K, dt, act=ACT_NONE, seed=0, offset=0.3):
+    """qkv / fc1 with the preceding LayerNorm folded into the epilogue (gemm.cu SPEC 5 / 6) against
+    F.layer_norm(x) W^T + b (+ GELU) in fp32; x16 + statistics come from rowstats_cast (the chain's first link)."""
+    x = _rand((M, K), seed, 1.5) + offset
+    lw = 1.0 + _rand((K,), seed + 1, 0.2)
+    lb = _rand((K,), seed + 2, 0.2)
+    W = _rand((N, K), seed + 3, 1.0 / math.sqrt(K))
+    b = _rand((N,), seed + 4)
+    ref = F.layer_norm(x, (K,), lw, lb, 1e-6) @ W.t() + b
+    if act == ACT_GELU:
+        ref = F.gelu(ref)
+    parts, part_cols = ops.rowstat_layout(M, K)
+    x16 = torch.empty(M, K, device=DEV, dtype=dt)
+    stats = torch.empty(M, parts, 2, device=DEV)
+    ops.rowstats_cast(x, x16, stats)
+    torch.cuda.synchronize()
+    assert torch.equal(x16, x.to(dt))
+    sref = _stats_ref(x, parts)
+    assert (stats[..., 0].double() - sref[..., 0]).abs().max().item() < 1e-4
+    assert ((stats[..., 1].double() - sref[..., 1]).abs() / (sref[..., 1] + 1e-6)).max().item() < 1e-3
+    wf = (W * lw[None, :]).to(dt).contiguous()
+    c1 = wf.float().sum(1).contiguous()
+    c2 = (W @ lb + b).contiguous()
+    out = torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(x16, wf, out, bias=c2, act=act, ln_fold=(stats, c1, 1e-6))
+    torch.cuda.synchronize()
+    # operand rounding of the un-normalised rows: one 16-bit rounding of x relative to its own magnitude, seen through
+    # rstd ~ 1/std(x); the plain path rounds LN(x) instead -- same order when |mean| is not far above std
+    return _err(out, ref), _tol(ref, dt) * (2.0 + abs(offset))
 
 
 def check_gemm_patch_rowmap(dt, frames=3, P=20, N=384, K=592, seed=0):
@@ -428,10 +493,10 @@ def check_align_chain(K, h, w, affine=True, seed=0):
     ref = torch.stack([anchors[0, 0], anchors[0, 2]])
     sc2 = torch.zeros(4 * ops.LSQ_MAX_PARTIALS, device=DEV, dtype=torch.float64)
     for k in range(1, K):
-        if affine:
-            ops.lsq_scale_shift(anchors[k, 0:2], ref, ss, sc2)
+        if affine:                     # (.clone(): 16-byte aligned like WindowAligner's own buffers, whatever hw is)
+            ops.lsq_scale_shift(anchors[k, 0:2].clone(), ref, ss, sc2)
         ref_t[k].copy_(ss)
-        ops.affine_clamp_blend(anchors[k, 2:3], ss, ref[1:2])
+        ops.affine_clamp_blend(anchors[k, 2:3].clone(), ss, ref[1:2])
     torch.cuda.synchronize()
     assert torch.equal(table, ref_t), f"chain table differs from the per-window kernels: {(table - ref_t).abs().max().item():.3e}"
     # oracle (numpy float32 sums): same recurrence on the host
@@ -460,6 +525,16 @@ CHECKS = [
     ("gemm 2740x4096x1024 fp16 gelu", lambda: check_gemm_plain(2740, 4096, 1024, HF, act=ACT_GELU)),
     ("gemm 20000x1152x384 bf16 many tiles", lambda: check_gemm_plain(20000, 1152, 384, BF)),
     ("gemm 1369x256x256 bf16 res h16 x2 + relu copy", lambda: check_gemm_plain(1369, 256, 256, BF, res1="h16", res2=True, out_relu=True)),
+    ("gemm 2740x1024x1024 bf16 residual + fold outputs (SPEC 4)", lambda: check_gemm_residual_fold_producer(2740, 1024, 1024, BF)),
+    ("gemm 43840x1024x1024 bf16 residual + fold outputs", lambda: check_gemm_residual_fold_producer(43840, 1024, 1024, BF)),
+    ("gemm 5000x1024x4096 fp16 residual + fold outputs", lambda: check_gemm_residual_fold_producer(5000, 1024, 4096, HF)),
+    ("gemm 30140x384x1536 bf16 residual + fold outputs (bn=192)", lambda: check_gemm_residual_fold_producer(30140, 384, 1536, BF)),
+    ("gemm 30140x384x384 fp16 residual + fold, mean=40", lambda: check_gemm_residual_fold_producer(30140, 384, 384, HF, offset=40.0)),
+    ("gemm 2740x3072x1024 bf16 LN fold (SPEC 5)", lambda: check_gemm_ln_fold(2740, 3072, 1024, BF)),
+    ("gemm 43840x4096x1024 bf16 LN fold + gelu (SPEC 6)", lambda: check_gemm_ln_fold(43840, 4096, 1024, BF, act=ACT_GELU)),
+    ("gemm 30140x1152x384 fp16 LN fold", lambda: check_gemm_ln_fold(30140, 1152, 384, HF)),
+    ("gemm 30140x1536x384 fp16 LN fold + gelu, mean=3", lambda: check_gemm_ln_fold(30140, 1536, 384, HF, act=ACT_GELU, offset=3.0)),
+    ("gemm 2740x1024x4096 bf16 ls+res f32 separate out (SPEC 3)", lambda: check_gemm_plain(2740, 1024, 4096, BF, gamma=True, res1="f32", out_f32=True, inplace=False)),
     ("gemm K tail 592 bf16", lambda: check_gemm_plain(500, 384, 592, BF)),
     ("gemm K=24 bf16 (single partial k-block)", lambda: check_gemm_plain(500, 64, 24, BF)),
     ("gemm patch-embed row map bf16", lambda: check_gemm_patch_rowmap(BF)),

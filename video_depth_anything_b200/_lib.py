@@ -31,6 +31,8 @@ class GemmParams(C.Structure):
         ("out_relu", C.c_void_p), ("row_group", C.c_int32), ("geglu_half", C.c_int32),
         ("convt_s", C.c_int32), ("convt_co", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
         ("tail_w", C.c_void_p), ("tail_b", C.c_float),
+        ("out16", C.c_void_p), ("row_stats_out", C.c_void_p), ("row_stats_in", C.c_void_p), ("ln_c1", C.c_void_p),
+        ("stat_parts", C.c_int32), ("stat_cols", C.c_int32), ("ln_eps", C.c_float),
     ]
 
 
@@ -39,8 +41,11 @@ _SIGS = {
     "vda_last_error": (C.c_char_p, []),
     "vda_device_query": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vda_gemm": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
+    "vda_gemm_rowstat_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vda_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int,
                                 C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vda_rowstats_cast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p]),
     "vda_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "vda_attention_spatial": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -53,6 +53,13 @@ struct GemmDev {
   const float* tail_w;
   float tail_b;
   int staged;   // LINEAR: transpose the tile through shared memory (fp32 residual / fp32 output streams)
+  // LayerNorm folding (see SPEC 4 / 5 / 6 in the kernel)
+  void* out16;              // SPEC 4: 16-bit copy of the fp32 output rows [M, ldo]
+  float2* stats_out;        // SPEC 4: per-row partial statistics [M][stat_parts] = (mean, M2) over stat_cols columns
+  const float2* stats_in;   // SPEC 5/6: the producer's partial statistics of the A rows
+  const float* ln_c1;       // SPEC 5/6: c1[n] = sum_k W'[n,k]  (W' = 16-bit(LayerNorm weight * W))
+  int stat_parts, stat_cols;
+  float ln_eps, ln_inv_d;
   int pair;     // host only: launch the cta_group::2 variant
   int prefetch_max_kb;   // residual L2 prefetch of the next tile only when the K loop has at most this many blocks
 };
@@ -139,8 +146,10 @@ constexpr uint32_t kStagingBytes = kEpiWarps * kStageTile;
 // drained by that CTA's own epilogue warps.
 template <typename T, int EPI, bool CONV, bool STAGED, int SPEC, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t rfull_bar[kEpiWarps][2];   // SPEC 4: residual chunk landed (per epilogue warp)
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
@@ -163,6 +172,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], (CTA2 ? 2 : 1) * kEpiWarps);   // one arrival per epilogue warp; pair: both CTAs
+    }
+    if (SPEC == 4) {
+      tma_prefetch_desc(&tmC);
+      for (int w = 0; w < kEpiWarps; ++w) { mbar_init(&rfull_bar[w][0], 1); mbar_init(&rfull_bar[w][1], 1); }
     }
     mbar_fence_init();
   }
@@ -287,7 +300,99 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int col_base = n_blk * p.block_n;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
 
-      if (EPI == VDA_EPI_TAIL) {   // block_n == N == 32: one dot product per row, thread = row (no staging)
+      if (EPI == VDA_EPI_LINEAR && SPEC == 4) {
+        // ---- fp32 residual stream updated in place, all global traffic of the tile by TMA (thread = row) ----
+        //   out[r, n] = (acc + bias[n]) * gamma[n] + out[r, n]          (proj / fc2 + LayerScale + residual)
+        // Each epilogue warp owns 32 rows x its half of the tile's columns, in chunks of 32 columns (a 32 x 32 fp32 box
+        // = 4 KB, SWIZZLE_128B: row r's 16-byte slot j sits at slot j ^ (r & 7), conflict-free for row-per-thread
+        // accesses).  The residual box of chunk k+2 is requested as soon as the result of chunk k has left its buffer
+        // (two buffers per warp, flat over this CTA's tiles, so the first chunks of the NEXT tile are in flight a whole
+        // tile ahead); results go back with TMA stores from the same buffer.  64 KB of loads in flight per SM without
+        // a single address register: the register-staged version (SPEC 3) was bound by the 32 KB its 8 warps could
+        // keep in flight (3.9 TB/s, tensor pipe 41 % active on proj).
+        // Optional LayerNorm folding for the consumer GEMM (SPEC 5 / 6): a 16-bit copy of the new rows and, per row and
+        // column half, (mean, M2) of the new values (shifted sums: M2 = sum d^2 - (sum d)^2 / n with d = v - v[first]).
+        const int r = q * 32 + lane;
+        const int nch32 = p.block_n >> 6;                       // 32-column chunks per warp (block_n % 64 == 0)
+        const int c_begin = eh * (p.block_n >> 1);
+        const uint32_t buf0 = smem_base + p.stages * p.stage_bytes + ew * 8192u;
+        uint64_t* rfull = rfull_bar[ew];
+        // flat chunk k of this warp: tile tile0 + (k / nch32) * tile_step, chunk k % nch32; buffer k & 1
+        auto issue_load = [&](uint32_t k) {
+          const int tl = tile0 + static_cast<int>(k / nch32) * tile_step;
+          if (tl >= p.num_tiles) return;
+          const int ci = static_cast<int>(k % nch32);
+          const int nb = tl % p.tiles_n;
+          const int mb = CTA2 ? 2 * (tl / p.tiles_n) + rank : tl / p.tiles_n;
+          mbar_arrive_expect_tx(&rfull[k & 1u], 4096u);
+          tma_load_2d(reinterpret_cast<void*>(smem_gen + (buf0 - smem_base) + (k & 1u) * 4096u), &tmC, &rfull[k & 1u],
+                      nb * p.block_n + c_begin + ci * 32, mb * BLOCK_M + q * 32);
+        };
+        if (tile == tile0) {                                    // first tile of this CTA: prime both buffers
+          if (elect_one()) { issue_load(0); issue_load(1); }
+          __syncwarp();
+        }
+        const uint32_t kbase = static_cast<uint32_t>((tile - tile0) / tile_step) * nch32;
+        const long long grow = static_cast<long long>(m_blk) * BLOCK_M + r;
+        const bool row_ok = grow < p.M;
+        float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+        float shift = 0.f;
+        for (int ci = 0; ci < nch32; ++ci) {
+          const uint32_t k = kbase + ci;
+          const uint32_t buf = buf0 + (k & 1u) * 4096u;
+          const int c0 = c_begin + ci * 32;
+          const int col = col_base + c0;
+          mbar_wait(&rfull[k & 1u], (k >> 1) & 1u);
+          if (ci == 0) {
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+          }
+          uint32_t rr[32];
+          tmem_ld32(t_row + c0, rr);
+          tmem_ld_wait32(rr);
+          uint32_t h16[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = buf + stg_off(lane, j);
+            const F4 res = lds128(a);
+            const F4 b4 = load4f(p.bias + col + 4 * j), g4 = load4f(p.gamma + col + 4 * j);   // warp-uniform addresses
+            F4 v;
+            v.a = __ffma2_rn(__fadd2_rn(make_float2(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1])), b4.a), g4.a, res.a);
+            v.b = __ffma2_rn(__fadd2_rn(make_float2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])), b4.b), g4.b, res.b);
+            sts128(a, __float_as_uint(v.a.x), __float_as_uint(v.a.y), __float_as_uint(v.b.x), __float_as_uint(v.b.y));
+            if (p.stats_out) {
+              if (ci == 0 && j == 0) shift = v.a.x;
+              const float2 sh2 = make_float2(shift, shift);
+              const float2 da = __fadd2_rn(v.a, make_float2(-sh2.x, -sh2.y)), db = __fadd2_rn(v.b, make_float2(-sh2.x, -sh2.y));
+              s1 = __fadd2_rn(s1, __fadd2_rn(da, db));
+              s2 = __ffma2_rn(da, da, s2);
+              s2 = __ffma2_rn(db, db, s2);
+            }
+            h16[2 * j] = H16<T>::pack2(v.a.x, v.a.y);
+            h16[2 * j + 1] = H16<T>::pack2(v.b.x, v.b.y);
+          }
+          if (p.out16 && row_ok) {
+            uint4* o16 = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out16) + grow * p.ldo + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o16[j] = make_uint4(h16[4 * j], h16[4 * j + 1], h16[4 * j + 2], h16[4 * j + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            tma_store_2d(&tmC, reinterpret_cast<const void*>(smem_gen + (buf - smem_base)), col, m_blk * BLOCK_M + q * 32);
+            bulk_commit();
+            bulk_wait_read<0>();          // the store has read the buffer: it may receive the residual of chunk k + 2
+            issue_load(k + 2);
+          }
+          __syncwarp();
+        }
+        if (p.stats_out && row_ok) {
+          const float n = static_cast<float>(p.block_n >> 1);
+          const float t1 = s1.x + s1.y, t2 = s2.x + s2.y;
+          const float md = t1 / n;
+          p.stats_out[grow * p.stat_parts + (n_blk * 2 + eh)] = make_float2(shift + md, fmaxf(t2 - t1 * md, 0.f));
+        }
+      } else if (EPI == VDA_EPI_TAIL) {   // block_n == N == 32: one dot product per row, thread = row (no staging)
         const int r = q * 32 + lane;
         bool valid;
         long long out_row;
@@ -488,9 +593,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // SPEC folds the run-time epilogue flags of the three hot encoder GEMMs at compile time (the generic
           // version spends more instructions on flag tests, uniform loads and branches than on arithmetic):
           //   1: bias -> 16 bit (qkv)   2: bias, GELU -> 16 bit (fc1)   3: bias, LayerScale, fp32 residual -> fp32 (proj, fc2)
+          //   5 / 6: as 1 / 2 with the preceding LayerNorm folded in (A holds the un-normalised 16-bit rows):
+          //          out = rstd_r * (acc - mu_r * c1[n]) + c2[n], (mu_r, rstd_r) from the producer's row statistics
+          constexpr bool fold = SPEC == 5 || SPEC == 6;
           const bool has_bias = SPEC != 0 ? true : p.bias != nullptr;
           const bool has_gamma = SPEC != 0 ? SPEC == 3 : p.gamma != nullptr;
-          const int act = SPEC != 0 ? (SPEC == 2 ? VDA_ACT_GELU : VDA_ACT_NONE) : p.act;
+          const int act = SPEC != 0 ? ((SPEC == 2 || SPEC == 6) ? VDA_ACT_GELU : VDA_ACT_NONE) : p.act;
           const bool has_res = SPEC != 0 ? SPEC == 3 : (p.res1 != nullptr && p.res1_f32);
           const bool out_f32 = SPEC != 0 ? SPEC == 3 : p.out_f32 != 0;
           const bool relu_copy = SPEC != 0 ? false : p.out_relu != nullptr;
@@ -510,6 +618,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             all_rows = all_rows && orow[it] >= 0;
           }
           all_rows = __all_sync(0xffffffffu, all_rows);   // warp-uniform: the common full-tile case stores without row tests
+          float rs_row[8], nm_row[8];                     // fold: rstd and -mu * rstd of the 8 rows of this lane
+          if (fold) {
+            // thread = row: Chan-merge the producer's partial (mean, M2) of row q*32 + lane, then hand the two scalars
+            // to the lanes that hold the row in the transposed passes
+            const long long grow = static_cast<long long>(m_blk) * BLOCK_M + q * 32 + lane;
+            float mean = 0.f, m2 = 0.f, n = 0.f;
+            if (grow < p.M) {
+              const float nb = static_cast<float>(p.stat_cols);
+              for (int i = 0; i < p.stat_parts; ++i) {
+                const float2 pm = p.stats_in[grow * p.stat_parts + i];
+                const float delta = pm.x - mean;
+                const float nn = n + nb;
+                mean += delta * (nb / nn);
+                m2 += pm.y + delta * delta * (n * nb / nn);
+                n = nn;
+              }
+            }
+            const float rstd = rsqrtf(m2 * p.ln_inv_d + p.ln_eps);
+            const float nm = -mean * rstd;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              rs_row[it] = __shfl_sync(0xffffffffu, rstd, it * 4 + rsub);
+              nm_row[it] = __shfl_sync(0xffffffffu, nm, it * 4 + rsub);
+            }
+          }
           // residual row segments are loaded one chunk ahead (the first one before the accumulator is ready), so
           // their HBM/L2 latency hides behind the TMEM drain and the math of the previous chunk
           F4 rnxt[8];
@@ -547,6 +680,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (col < p.N && (c0 + 32 <= c_end || cg < 4)) {
               if (has_bias) bias_nxt = load4f(p.bias + col);
               if (has_gamma) gamma_nxt = load4f(p.gamma + col);
+              if (fold) gamma_nxt = load4f(p.ln_c1 + col);
             }
           };
           if (c_begin < c_end) load_bg(c_begin);
@@ -583,7 +717,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int it = 0; it < 8; ++it) v[it] = lds128(stg + stg_off(it * 4 + rsub, cg));
               const F4 bias4 = bias_nxt, gamma4 = gamma_nxt;
               if (c0 + 32 < c_end) load_bg(c0 + 32);
-              if (has_bias) {
+              if (fold) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {   // rstd * acc + (-mu rstd * c1 + c2)
+                  const float2 nm2 = make_float2(nm_row[it], nm_row[it]), rs2 = make_float2(rs_row[it], rs_row[it]);
+                  v[it].a = __ffma2_rn(v[it].a, rs2, __ffma2_rn(nm2, gamma4.a, bias4.a));
+                  v[it].b = __ffma2_rn(v[it].b, rs2, __ffma2_rn(nm2, gamma4.b, bias4.b));
+                }
+              } else if (has_bias) {
 #pragma unroll
                 for (int it = 0; it < 8; ++it) v[it] = add4(v[it], bias4);
               }
@@ -703,6 +844,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
+    if (EPI == VDA_EPI_LINEAR && SPEC == 4) {   // this lane's TMA stores have completed before the CTA retires
+      if (elect_one()) bulk_wait<0>();
+      __syncwarp();
+    }
   }
 
   tc_fence_before();
@@ -739,7 +884,9 @@ int make_tensor_map(CUtensorMap* m, int dtype, const void* base, int rank, const
   PFN_encodeTiled enc = get_encode();
   VDA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, dtype == VDA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+  const CUtensorMapDataType cdt = dtype == kTmapF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                  : (dtype == VDA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  CUresult r = enc(m, cdt,
                    static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims, strides_bytes, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -795,7 +942,8 @@ static int pick_block_n(int N, int tiles_m) {
 }
 
 template <typename T, int EPI, bool CONV, bool STAGED, int SPEC, bool CTA2>
-static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, size_t smem, cudaStream_t st) {
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmDev& d, size_t smem,
+                   cudaStream_t st) {
   auto kfn = gemm_kernel<T, EPI, CONV, STAGED, SPEC, CTA2>;
   VDA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kfn), smem));   // per (kernel, device)
   const bool pdl = pdl_enabled();
@@ -825,49 +973,69 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  VDA_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, d));
+  VDA_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, tmC, d));
   VDA_CUDA(cudaGetLastError());
   return 0;
 }
+struct Maps { CUtensorMap a, b, c; };   // c: fp32 residual / output tile map (SPEC 4 only; else a copy of a)
 template <typename T, int EPI, bool CONV, bool STAGED, int SPEC = 0>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d, size_t smem, cudaStream_t st) {
-  if (d.pair) return launch2<T, EPI, CONV, STAGED, SPEC, true>(tmA, tmB, d, smem, st);
-  return launch2<T, EPI, CONV, STAGED, SPEC, false>(tmA, tmB, d, smem, st);
+static int launch(const Maps& tm, const GemmDev& d, size_t smem, cudaStream_t st) {
+  if (d.pair) return launch2<T, EPI, CONV, STAGED, SPEC, true>(tm.a, tm.b, tm.c, d, smem, st);
+  return launch2<T, EPI, CONV, STAGED, SPEC, false>(tm.a, tm.b, tm.c, d, smem, st);
 }
 
 template <typename T>
-static int dispatch(const vda_gemm_params* p, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& d,
-                    size_t smem, cudaStream_t st) {
+static int dispatch(const vda_gemm_params* p, const Maps& tm, const GemmDev& d, int spec, size_t smem, cudaStream_t st) {
   const bool conv = p->a_mode == VDA_A_CONV3;
   switch (p->epilogue) {
     case VDA_EPI_LINEAR:
-      if (d.staged && !conv) {
-        // compile-time specialisations of the hot encoder epilogues (see SPEC in the kernel)
-        const bool plain16 = p->bias && !p->res1 && !p->res2 && !p->out_f32 && !p->out_relu && !p->gamma &&
-                             p->row_group == 0;
-        if (plain16 && p->act == VDA_ACT_NONE) return launch<T, VDA_EPI_LINEAR, false, true, 1>(tmA, tmB, d, smem, st);
-        if (plain16 && p->act == VDA_ACT_GELU) return launch<T, VDA_EPI_LINEAR, false, true, 2>(tmA, tmB, d, smem, st);
-        if (p->bias && p->gamma && p->res1 && p->res1_f32 && !p->res2 && p->out_f32 && !p->out_relu &&
-            p->act == VDA_ACT_NONE && p->row_group == 0)
-          return launch<T, VDA_EPI_LINEAR, false, true, 3>(tmA, tmB, d, smem, st);
+      // compile-time specialisations of the hot encoder epilogues (see SPEC in the kernel; chosen by pick_spec)
+      switch (spec) {
+        case 1: return launch<T, VDA_EPI_LINEAR, false, true, 1>(tm, d, smem, st);
+        case 2: return launch<T, VDA_EPI_LINEAR, false, true, 2>(tm, d, smem, st);
+        case 3: return launch<T, VDA_EPI_LINEAR, false, true, 3>(tm, d, smem, st);
+        case 4: return launch<T, VDA_EPI_LINEAR, false, true, 4>(tm, d, smem, st);
+        case 5: return launch<T, VDA_EPI_LINEAR, false, true, 5>(tm, d, smem, st);
+        case 6: return launch<T, VDA_EPI_LINEAR, false, true, 6>(tm, d, smem, st);
+        default: break;
       }
       if (d.staged)
-        return conv ? launch<T, VDA_EPI_LINEAR, true, true>(tmA, tmB, d, smem, st)
-                    : launch<T, VDA_EPI_LINEAR, false, true>(tmA, tmB, d, smem, st);
-      return conv ? launch<T, VDA_EPI_LINEAR, true, false>(tmA, tmB, d, smem, st)
-                  : launch<T, VDA_EPI_LINEAR, false, false>(tmA, tmB, d, smem, st);
+        return conv ? launch<T, VDA_EPI_LINEAR, true, true>(tm, d, smem, st)
+                    : launch<T, VDA_EPI_LINEAR, false, true>(tm, d, smem, st);
+      return conv ? launch<T, VDA_EPI_LINEAR, true, false>(tm, d, smem, st)
+                  : launch<T, VDA_EPI_LINEAR, false, false>(tm, d, smem, st);
     case VDA_EPI_GEGLU:
       VDA_CHECK(!conv, "GEGLU epilogue is only defined for plain GEMMs");
-      return launch<T, VDA_EPI_GEGLU, false, true>(tmA, tmB, d, smem, st);
+      return launch<T, VDA_EPI_GEGLU, false, true>(tm, d, smem, st);
     case VDA_EPI_CONVT:
       VDA_CHECK(!conv, "CONVT epilogue is only defined for plain GEMMs");
-      return launch<T, VDA_EPI_CONVT, false, false>(tmA, tmB, d, smem, st);
+      return launch<T, VDA_EPI_CONVT, false, false>(tm, d, smem, st);
     case VDA_EPI_TAIL:
-      return conv ? launch<T, VDA_EPI_TAIL, true, false>(tmA, tmB, d, smem, st)
-                  : launch<T, VDA_EPI_TAIL, false, false>(tmA, tmB, d, smem, st);
+      return conv ? launch<T, VDA_EPI_TAIL, true, false>(tm, d, smem, st)
+                  : launch<T, VDA_EPI_TAIL, false, false>(tm, d, smem, st);
   }
   set_error("unknown epilogue %d", p->epilogue);
   return 1;
+}
+
+// Which compile-time specialised epilogue serves this problem (0 = generic).  block_n is known.
+static int pick_spec(const vda_gemm_params* p, const GemmDev& d) {
+  if (p->epilogue != VDA_EPI_LINEAR || !d.staged || p->a_mode == VDA_A_CONV3) return 0;
+  const bool plain16 = p->bias && !p->res1 && !p->res2 && !p->out_f32 && !p->out_relu && !p->gamma && p->row_group == 0;
+  if (plain16 && p->row_stats_in) return p->act == VDA_ACT_GELU ? 6 : (p->act == VDA_ACT_NONE ? 5 : 0);
+  if (plain16 && p->act == VDA_ACT_NONE) return 1;
+  if (plain16 && p->act == VDA_ACT_GELU) return 2;
+  if (p->bias && p->gamma && p->res1 && p->res1_f32 && !p->res2 && p->out_f32 && !p->out_relu && p->act == VDA_ACT_NONE &&
+      p->row_group == 0) {
+    // fp32 residual stream: all tile traffic by TMA when the residual is updated in place and the tile geometry allows
+    // 32-column boxes (SPEC 4); VDA_GEMM_TMA_EPI=0 keeps the register-staged epilogue (SPEC 3) for A/B runs
+    static const char* e = getenv("VDA_GEMM_TMA_EPI");
+    const bool tma_ok = !(e && e[0] == '0') && p->res1 == p->out && p->ldr1 == p->ldo && d.block_n % 64 == 0 &&
+                        p->N % d.block_n == 0 && (p->ldo % 4) == 0;
+    if (tma_ok) return 4;
+    return (p->out16 || p->row_stats_out) ? -1 : 3;
+  }
+  return 0;
 }
 
 }  // namespace vda
@@ -892,7 +1060,9 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
     static const char* pf = getenv("VDA_GEMM_PREFETCH_KB");     // debug hook (tools/bench_gemm.py)
     d.prefetch_max_kb = pf ? atoi(pf) : 32;
   }
-  CUtensorMap tmA, tmB;
+  Maps tm;
+  CUtensorMap& tmA = tm.a;
+  CUtensorMap& tmB = tm.b;
 
   if (conv) {
     VDA_CHECK(p->C % 64 == 0 && p->K == 9 * p->C, "conv mode needs C %% 64 == 0 and K == 9*C (C=%d K=%d)", p->C, p->K);
@@ -973,7 +1143,13 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
     static const char* force = getenv("VDA_GEMM_STAGED");
     if (force && (force[0] == '0' || force[0] == '1')) d.staged = force[0] - '0';
   }
-  const uint32_t staging = d.staged ? kStagingBytes : 0u;
+  const int spec = pick_spec(p, d);
+  VDA_CHECK(spec >= 0, "out16 / row_stats_out need the in-place fp32 residual epilogue with N %% block_n == 0 and "
+                       "block_n %% 64 == 0 (N=%d block_n=%d)", p->N, d.block_n);
+  VDA_CHECK(spec == 4 || (!p->out16 && !p->row_stats_out), "out16 / row_stats_out: unsupported epilogue combination");
+  VDA_CHECK((spec == 5 || spec == 6) == (p->row_stats_in != nullptr), "row_stats_in: unsupported epilogue combination");
+  // epilogue staging: 8 transposition tiles of 4 KB, or (SPEC 4) 8 x 2 TMA boxes of 4 KB
+  const uint32_t staging = spec == 4 ? kEpiWarps * 8192u : (d.staged ? kStagingBytes : 0u);
   int stages = static_cast<int>((227u * 1024u - 1024u - 512u - staging) / d.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   d.stages = stages;
@@ -990,7 +1166,44 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
   d.convt_s = p->convt_s; d.convt_co = p->convt_co; d.in_h = p->in_h; d.in_w = p->in_w;
   d.tail_w = p->tail_w; d.tail_b = p->tail_b;
 
+  tm.c = tm.a;
+  if (spec == 4) {
+    cuuint64_t dims[2] = {(cuuint64_t)p->N, (cuuint64_t)p->M};
+    cuuint64_t strides[1] = {(cuuint64_t)p->ldo * 4};
+    cuuint32_t box[2] = {32, 32};
+    if (make_tensor_map(&tm.c, kTmapF32, p->out, 2, dims, strides, box)) return 1;
+    d.out16 = p->out16;
+    d.stats_out = reinterpret_cast<float2*>(p->row_stats_out);
+    d.stat_parts = 2 * d.tiles_n;
+    d.stat_cols = d.block_n / 2;
+    VDA_CHECK(!p->row_stats_out || p->stat_parts == d.stat_parts,
+              "row_stats_out: caller expects %d parts, the kernel writes %d (see vda_gemm_rowstat_layout)", p->stat_parts,
+              d.stat_parts);
+  }
+  if (spec == 5 || spec == 6) {
+    VDA_CHECK(p->ln_c1 && p->stat_parts > 0 && p->stat_cols > 0 && p->stat_parts * p->stat_cols == p->K,
+              "LayerNorm fold: need ln_c1 and a statistics layout covering K (parts %d x cols %d, K %d)", p->stat_parts,
+              p->stat_cols, p->K);
+    d.stats_in = reinterpret_cast<const float2*>(p->row_stats_in);
+    d.ln_c1 = p->ln_c1;
+    d.stat_parts = p->stat_parts;
+    d.stat_cols = p->stat_cols;
+    d.ln_eps = p->ln_eps;
+    d.ln_inv_d = 1.f / static_cast<float>(p->K);
+  }
+
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->dtype == VDA_BF16) return dispatch<__nv_bfloat16>(p, tmA, tmB, d, smem, st);
-  return dispatch<__half>(p, tmA, tmB, d, smem, st);
+  if (p->dtype == VDA_BF16) return dispatch<__nv_bfloat16>(p, tm, d, spec, smem, st);
+  return dispatch<__half>(p, tm, d, spec, smem, st);
+}
+
+// Layout of the per-row partial statistics a GEMM with row_stats_out writes for an [M, N] output: `parts` partials
+// per row, each over `part_cols` consecutive columns (the column halves of the kernel's N tiles).
+extern "C" int vda_gemm_rowstat_layout(int M, int N, int* parts, int* part_cols) {
+  VDA_CHECK(M > 0 && N > 0 && parts && part_cols, "bad arguments");
+  const int bn = pick_block_n(N, (M + BLOCK_M - 1) / BLOCK_M);
+  VDA_CHECK(bn % 64 == 0 && N % bn == 0, "no row-statistics layout for N=%d (block_n=%d)", N, bn);
+  *parts = 2 * (N / bn);
+  *part_cols = bn / 2;
+  return 0;
 }

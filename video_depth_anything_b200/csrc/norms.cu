@@ -80,6 +80,43 @@ layernorm_kernel(const void* __restrict__ in, T* __restrict__ out, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row statistics + 16-bit copy of an fp32 row matrix, in the layout the residual GEMM epilogue (gemm.cu SPEC 4) writes:
+// per row, `parts` partials (mean, M2) over `part_cols` consecutive columns each.  Used once per forward for the token
+// matrix after patch embedding; every later LayerNorm input of the encoder comes out of a proj / fc2 epilogue.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+rowstats_cast_kernel(const float* __restrict__ in, T* __restrict__ out16, float2* __restrict__ stats, long long rows,
+                     int C, int parts, int part_cols) {
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* src = in + row * C;
+  for (int pt = 0; pt < parts; ++pt) {
+    const int c0 = pt * part_cols;
+    const float shift = src[c0];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = 4 * lane; c < part_cols; c += 128) {        // part_cols % 4 == 0
+      const float4 v = *reinterpret_cast<const float4*>(src + c0 + c);
+      const float dx = v.x - shift, dy = v.y - shift, dz = v.z - shift, dw = v.w - shift;
+      s1 += (dx + dy) + (dz + dw);
+      s2 += dx * dx + dy * dy + dz * dz + dw * dw;
+      uint2 u;
+      u.x = H16<T>::pack2(v.x, v.y);
+      u.y = H16<T>::pack2(v.z, v.w);
+      *reinterpret_cast<uint2*>(out16 + row * C + c0 + c) = u;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      const float md = s1 / part_cols;
+      stats[row * parts + pt] = make_float2(shift + md, fmaxf(s2 - s1 * md, 0.f));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // GroupNorm over [frames, hw, C] (NHWC).  Pass 1: every CTA reduces a slab of pixels of one frame to per-group
 // (mean, M2 = sum of squared deviations) partials; pass 1b merges the slabs of a frame in a fixed order with Chan's
 // parallel-variance update (no atomics anywhere: results are bit-reproducible run to run); pass 2: normalise + affine.
@@ -213,6 +250,23 @@ extern "C" int vda_layernorm(const void* in, int in_f32, void* out, const float*
     if (in_f32) LN_LAUNCH(__half, true); else LN_LAUNCH(__half, false);
   }
 #undef LN_LAUNCH
+  VDA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vda_rowstats_cast(const float* in, void* out16, float* stats, int64_t rows, int C, int parts, int part_cols,
+                                 int dtype, void* stream) {
+  VDA_CHECK(rows > 0 && parts > 0 && part_cols > 0 && parts * part_cols == C && part_cols % 4 == 0,
+            "rowstats_cast: bad layout (C=%d parts=%d part_cols=%d)", C, parts, part_cols);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+  if (dtype == VDA_BF16)
+    rowstats_cast_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, st>>>(in, static_cast<__nv_bfloat16*>(out16),
+                                                                  reinterpret_cast<float2*>(stats), rows, C, parts, part_cols);
+  else
+    rowstats_cast_kernel<__half><<<grid, wpb * 32, 0, st>>>(in, static_cast<__half*>(out16), reinterpret_cast<float2*>(stats),
+                                                           rows, C, parts, part_cols);
   VDA_CUDA(cudaGetLastError());
   return 0;
 }

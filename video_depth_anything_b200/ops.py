@@ -42,9 +42,18 @@ def _count(n=1):
     LAUNCHES += n
 
 
+def rowstat_layout(M: int, N: int):
+    """(parts, part_cols) of the per-row partial statistics a residual GEMM with `row_stats` writes for an [M, N] output."""
+    lib = _lib.load()
+    a, b = C.c_int(0), C.c_int(0)
+    check(lib.vda_gemm_rowstat_layout(M, N, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
 def gemm(a: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, bias=None, gamma=None, act=ACT_NONE,
          res1=None, res2=None, out_relu=None, row_group=0, epilogue=EPI_LINEAR,
-         conv_shape=None, geglu_half=0, convt=None, tail_w=None, tail_b=0.0, M=None) -> torch.Tensor:
+         conv_shape=None, geglu_half=0, convt=None, tail_w=None, tail_b=0.0, M=None,
+         out16=None, row_stats_out=None, ln_fold=None) -> torch.Tensor:
     """out = epilogue(a @ wt.T).  a: [M,K] h16 (row stride allowed) or NHWC [n,H,W,C] with conv_shape=(n,H,W,C);
     wt: [N,K] h16 contiguous.  Replaces F.linear / F.conv2d(1x1, 3x3 s1 p1) / F.conv_transpose2d(k == s)."""
     lib = _lib.load()
@@ -88,6 +97,23 @@ def gemm(a: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, bias=None, gam
     p.geglu_half = geglu_half
     if convt is not None:
         p.convt_s, p.convt_co, p.in_h, p.in_w = convt
+    if out16 is not None or row_stats_out is not None:
+        # producer side of the LayerNorm fold: h16 copy of the new fp32 rows + per-row partial (mean, M2)
+        if out16 is not None:
+            assert out16.dtype == a.dtype and out16.stride(-2) == p.ldo and out16.stride(-1) == 1
+            p.out16 = _p(out16)
+        if row_stats_out is not None:
+            assert row_stats_out.dtype == torch.float32 and row_stats_out.is_contiguous() and row_stats_out.shape[-1] == 2
+            p.row_stats_out, p.stat_parts = _p(row_stats_out), row_stats_out.shape[-2]
+    if ln_fold is not None:
+        # consumer side: ln_fold = (row_stats [M, parts, 2] fp32, c1 [N] fp32, eps); `a` holds the un-normalised rows,
+        # `wt` the LayerNorm-weight-scaled matrix, `bias` = W @ ln_bias + b
+        stats, c1, eps = ln_fold
+        assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.shape[-1] == 2 and c1.dtype == torch.float32
+        p.row_stats_in, p.ln_c1, p.ln_eps = _p(stats), _p(c1), float(eps)
+        p.stat_parts = stats.shape[-2]
+        assert K % p.stat_parts == 0
+        p.stat_cols = K // p.stat_parts
     if PROFILE is not None:
         _INFO.update(kind=("conv3x3" if conv_shape is not None else "gemm") + f"/epi{epilogue}",
                      M=int(p.M), N=int(N), K=int(K), flops=2.0 * p.M * N * K)
@@ -110,6 +136,21 @@ def layernorm(x: torch.Tensor, w, b, eps: float, out: torch.Tensor, *, drop_grou
                             0 if pe is None else (pe_frames or pe.shape[0]), _stream()))
     _count()
     return out
+
+
+def rowstats_cast(x: torch.Tensor, out16: torch.Tensor, stats: torch.Tensor):
+    """fp32 rows [M, C] -> h16 copy + per-row partial statistics [M, parts, 2] (start of the LayerNorm-fold chain)."""
+    lib = _lib.load()
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    parts = stats.shape[-2]
+    assert x.is_contiguous() and x.dtype == torch.float32 and out16.is_contiguous() and stats.is_contiguous()
+    assert stats.dtype == torch.float32 and Cc % parts == 0
+    if PROFILE is not None:
+        _INFO.update(kind="rowstats_cast", bytes=float(x.numel() * 4 + out16.numel() * 2))
+    check(lib.vda_rowstats_cast(_p(x), _p(out16), _p(stats), rows, Cc, parts, Cc // parts, dt_code(out16.dtype), _stream()))
+    _count()
+    return out16
 
 
 def groupnorm(x: torch.Tensor, w, b, eps: float, out: torch.Tensor, frames: int, hw: int, groups: int = 32):
@@ -293,7 +334,7 @@ def _profiled(fn, name):
     return wrapper
 
 
-for _n in ("preprocess_frames", "copy_frames", "gemm", "layernorm", "groupnorm", "attention_spatial", "attention_temporal", "patch_im2col", "write_cls",
+for _n in ("preprocess_frames", "copy_frames", "gemm", "layernorm", "rowstats_cast", "groupnorm", "attention_spatial", "attention_temporal", "patch_im2col", "write_cls",
            "pos_embed_bicubic", "im2col3x3_s2", "bilinear_nhwc", "tail_fused", "bilinear_f32", "add_h16", "lsq_scale_shift", "align_chain",
            "affine_clamp_blend"):
     globals()[_n] = _profiled(globals()[_n], _n)

@@ -201,7 +201,7 @@ class FeatureCache:
         self.eng, self.up, self.nh, self.nw = eng, up, nh, nw
         self.hp, self.wp = nh // 14, nw // 14
         P = self.hp * self.wp
-        self.store = [torch.empty(INFER_LEN, P, eng.D, dtype=eng.dtype, device=eng.device) for _ in range(4)]
+        self.store = [torch.empty(INFER_LEN, P, eng.D, dtype=eng.hdtype, device=eng.device) for _ in range(4)]   # taps: head operand type
         self.encoded = 0                                  # frames that went through the encoder (for reporting)
         # The slot bookkeeping depends on the window list only, so the index lists of ALL windows are planned on the
         # host now and uploaded once: per window [uploaded-frame index of each new frame | its cache slot | slot of
