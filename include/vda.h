@@ -161,6 +161,22 @@ int vda_copy_frames(const void* src, const int32_t* src_idx, void* dst, const in
 int vda_eval_sequence(const float* pred, const void* gt, int gt_f64, int frames, int64_t hw, double max_depth, double* out,
                       double* scale_shift, double* scratch, void* stream);
 
+/* Temporal alignment error (benchmark/eval/eval_tae.py:60-107 tae_torch, :109-213 eval_TAE).
+ * vda_eval_aligned_depth: out[i] = clip(1 / clip(scale * clip(pred[i], 1e-3) + shift, 1e-3), 1e-3, max_depth) in double
+ * (eval_tae.py:152-160), scale_shift from vda_eval_sequence.
+ * vda_eval_tae: `jobs` ordered frame pairs; job j un-projects depth[src_idx[j]] (double [frames, H*W]) with the pinhole
+ * intrinsics, applies the rigid motion, projects, rounds (half to even) and scatters the transformed depth into frame
+ * dst_idx[j] with the reference's last-writer rule for duplicate targets (largest source index wins: exact integer
+ * atomicMax, then a deterministic gather), and returns in out[j] the mean of |depth_dst - proj| / depth_dst over pixels
+ * with proj > 0, depth_dst > 0 and masks[dst] != 0 (masks: uint8 [frames, H*W] or NULL), 0 if there is none.
+ * params: double [jobs, 16] = R (row-major 3x3), t (3), fx, fy, cx, cy.  winners: int32 scratch [jobs, H*W];
+ * partials: double scratch [jobs, VDA_EVAL_SLABS, 2]. */
+int vda_eval_aligned_depth(const float* pred, const double* scale_shift, double max_depth, int64_t n, double* out,
+                           void* stream);
+int vda_eval_tae(const double* depth, const uint8_t* masks, const double* params, const int32_t* src_idx,
+                 const int32_t* dst_idx, int jobs, int H, int W, int32_t* winners, double* partials, double* out,
+                 void* stream);
+
 /* im2col of the 14x14/14 patch-embed conv (patch_embed.py:66,76): x fp32 [frames,3,H,W] ->
  * A h16 [frames*hp*wp, kpad], column = c*196 + ky*14 + kx, zero padded to kpad. */
 int vda_patch_im2col(const float* x, void* A, int frames, int H, int W, int kpad, int dtype, void* stream);

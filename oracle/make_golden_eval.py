@@ -31,6 +31,71 @@ def import_reference_eval():
     return ev
 
 
+def import_reference_tae():
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.path.insert(0, REF)
+    import torch
+    torch.set_num_threads(1)                   # index_put with repeated indices: sequential = last writer wins
+    import benchmark.eval.eval_tae as tae
+    tae.device = torch.device("cpu")
+    return tae
+
+
+def synth_tae_case(seed, T, H, W, max_depth, motion, masked):
+    """A smooth positive depth sequence seen by a slowly moving pinhole camera (poses camera-to-world)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    gts, poses, Ks = [], [], []
+    for t in range(T):
+        gt = 2.5 + 1.2 * np.sin(xx / 9.0 + 0.3 * t) * np.cos(yy / 7.0) + 0.05 * rng.standard_normal((H, W))
+        gt[rng.random((H, W)) < 0.05] = 0.0                       # holes in the ground truth
+        gts.append(gt)
+        ang = motion * 0.03 * t + 0.01 * rng.standard_normal(3)
+        Rx = np.array([[1, 0, 0], [0, np.cos(ang[0]), -np.sin(ang[0])], [0, np.sin(ang[0]), np.cos(ang[0])]])
+        Ry = np.array([[np.cos(ang[1]), 0, np.sin(ang[1])], [0, 1, 0], [-np.sin(ang[1]), 0, np.cos(ang[1])]])
+        Rz = np.array([[np.cos(ang[2]), -np.sin(ang[2]), 0], [np.sin(ang[2]), np.cos(ang[2]), 0], [0, 0, 1]])
+        P = np.eye(4)
+        P[:3, :3] = Rz @ Ry @ Rx
+        P[:3, 3] = motion * np.array([0.05 * t, -0.02 * t, 0.04 * t]) + 0.01 * rng.standard_normal(3)
+        poses.append(P)
+        Ks.append(np.array([[0.9 * W, 0, W / 2.0 - 0.5], [0, 0.9 * W, H / 2.0 - 0.5], [0, 0, 1.0]]))
+    gts = np.stack(gts)
+    inf = (0.8 / np.maximum(gts, 0.3) + 0.07 + 0.01 * rng.standard_normal(gts.shape)).astype(np.float32)
+    masks = (rng.random(gts.shape) > 0.3) if masked else None
+    return inf, gts, np.stack(Ks), np.stack(poses), masks
+
+
+def make_tae_goldens(man):
+    import cv2
+    from oracle import eval_oracle as E
+    tae = import_reference_tae()
+    for name, (seed, T, H, W, md, motion, masked) in {"tae_T4_48x64": (10, 4, 48, 64, 10.0, 1.0, False),
+                                                       "tae_T3_37x53_fast": (11, 3, 37, 53, 10.0, 6.0, False),
+                                                       "tae_T5_40x40_masked": (12, 5, 40, 40, 4.0, 2.0, True)}.items():
+        inf, gt, Ks, poses, masks = synth_tae_case(seed, T, H, W, md, motion, masked)
+        with tempfile.TemporaryDirectory() as d:
+            ip, gp, mp_ = [], [], []
+            for t in range(T):
+                ip.append(os.path.join(d, f"i{t}.npy"))
+                gp.append(os.path.join(d, f"g{t}.npy"))
+                np.save(ip[-1], inf[t])
+                np.save(gp[-1], gt[t])
+                if masked:
+                    mp_.append(os.path.join(d, f"m{t}.png"))
+                    cv2.imwrite(mp_[-1], (masks[t] * 255).astype(np.uint8))
+            args = types.SimpleNamespace(max_depth_eval=md, a=0, b=H, c=0, d=W, mask=masked, hard_crop=False)
+            ref = float(tae.eval_TAE(ip, gp, [1.0] * T, mp_, list(Ks), list(poses), args))
+        mine = E.eval_tae(inf, gt, Ks, poses, md, masks)
+        err = abs(ref - mine)
+        print(name, ref, mine, err)
+        assert err < 1e-9 * max(1.0, abs(ref)), err
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), inf=inf, gt=gt, Ks=Ks, poses=poses,
+                            masks=(masks if masked else np.zeros(0, bool)), tae=np.array(ref, dtype=np.float64))
+        man[name] = {"max_depth": md, "tae": ref, "masked": masked, "oracle_vs_ref_abs": err}
+
+
 def synth_case(seed, T, H, W, max_depth, holes):
     rng = np.random.default_rng(seed)
     gt = (rng.random((T, H, W)) * (max_depth * 1.2) + 0.05).astype(np.float64)
@@ -67,8 +132,10 @@ def main():
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), inf=inf, gt=np.where(gt == 0, -1.0, gt),
                             metrics=np.array(ref, dtype=np.float64))
         man[name] = {"max_depth": md, "metrics": ref, "oracle_vs_ref_max_abs": err}
-    json.dump({"generator": "oracle/make_golden_eval.py", "cases": man}, open(os.path.join(GOLD, "EVAL_MANIFEST.json"), "w"),
-              indent=1)
+    tman = {}
+    make_tae_goldens(tman)
+    json.dump({"generator": "oracle/make_golden_eval.py", "cases": man, "tae_cases": tman},
+              open(os.path.join(GOLD, "EVAL_MANIFEST.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -53,3 +53,53 @@ def test_eval_edge_cases():
         eval_sequence(np.ones((2, 8, 8), np.float32), np.ones((2, 8, 9)), 10.0)
     with pytest.raises(RuntimeError):
         eval_sequence(np.ones((2, 8, 8), np.float32), gt, 10.0, device="cpu")
+
+
+# ------------------------------------------------------------------------------------------------ temporal alignment error
+TAE = json.load(open(os.path.join(GOLD, "EVAL_MANIFEST.json"))).get("tae_cases", {})
+
+
+@pytest.mark.parametrize("name", sorted(TAE))
+def test_tae_vs_reference_golden(name):
+    """Device TAE (vda_eval_tae: exact integer last-writer scatter + float64 gather) against the number the reference's
+    own eval_TAE / tae_torch produced (benchmark/eval/eval_tae.py, run single-threaded on the CPU by
+    oracle/make_golden_eval.py)."""
+    from video_depth_anything_b200.evaluate import eval_tae
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    masks = g["masks"] if TAE[name]["masked"] else None
+    got = eval_tae(g["inf"], g["gt"], g["Ks"], g["poses"], TAE[name]["max_depth"], masks)
+    ref = float(g["tae"])
+    assert abs(got - ref) <= 1e-9 * max(1.0, abs(ref)), (got, ref)
+    assert eval_tae(g["inf"], g["gt"], g["Ks"], g["poses"], TAE[name]["max_depth"], masks) == got      # bit-reproducible
+
+
+@pytest.mark.parametrize("T,H,W,motion,masked", [(6, 240, 320, 2.0, False), (4, 464, 618, 1.0, True), (3, 33, 47, 8.0, False)])
+def test_tae_vs_oracle_seeded(T, H, W, motion, masked):
+    """Larger seeded sequences (ScanNet's cropped 464 x 618 among them) against the oracle restatement; several jobs per
+    launch and a chunked job list (jobs_per_call=3) must give the same number."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    from make_golden_eval import synth_tae_case
+    from oracle import eval_oracle as E
+    from video_depth_anything_b200.evaluate import eval_tae
+    inf, gt, Ks, poses, masks = synth_tae_case(100 + T, T, H, W, 10.0, motion, masked)
+    ref = E.eval_tae(inf, gt, Ks, poses, 10.0, masks)
+    got = eval_tae(inf, gt, Ks, poses, 10.0, masks)
+    assert abs(got - ref) <= 1e-9 * max(1.0, abs(ref)), (got, ref)
+    assert eval_tae(inf, gt, Ks, poses, 10.0, masks, jobs_per_call=3) == got
+
+
+def test_tae_edge_cases():
+    from video_depth_anything_b200.evaluate import eval_tae
+    K = np.array([[50.0, 0, 16], [0, 50.0, 12], [0, 0, 1]])
+    Ks, eye = np.stack([K] * 3), np.stack([np.eye(4)] * 3)
+    inf = np.full((3, 24, 32), 0.5, np.float32)
+    gt = np.full((3, 24, 32), 2.0)
+    assert eval_tae(inf, gt, Ks, eye, 10.0) == 0.0                      # static camera, constant depth: perfect consistency
+    far = eye.copy()
+    far[1, :3, 3] = 1e6                                                  # nothing re-projects into the frame: tae_torch returns 0
+    assert eval_tae(inf, gt, Ks, far, 10.0) == 0.0
+    with pytest.raises(ValueError):
+        eval_tae(inf[:1], gt[:1], Ks[:1], eye[:1], 10.0)
+    with pytest.raises(RuntimeError):
+        eval_tae(inf, gt, Ks, eye, 10.0, device="cpu")

@@ -36,6 +36,10 @@
 #include "../../include/vda.h"
 #include "common.cuh"
 
+#ifndef VDA_SA_DEFAULT_KERNEL
+#define VDA_SA_DEFAULT_KERNEL 2
+#endif
+
 namespace vda {
 
 namespace sa {
@@ -547,6 +551,10 @@ spatial_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const SaP
 
 }  // namespace vda
 
+namespace vda {
+int sa4_launch(const void* qkv, void* out, int frames, int N, int heads, int dtype, cudaStream_t st);   // attention_spatial4.cu
+}
+
 using namespace vda;
 
 #ifdef VDA_SA_TIMING
@@ -562,6 +570,11 @@ extern "C" int vda_attention_spatial(const void* qkv, void* out, int frames, int
   VDA_CHECK(dtype == VDA_BF16 || dtype == VDA_FP16, "bad dtype %d", dtype);
   VDA_CHECK((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
             "qkv/out must be 16-byte aligned");
+  {
+    // VDA_SA_KERNEL=4: four streams x 64-key tiles (attention_spatial4.cu); 2: two streams x 128-key tiles (this file)
+    static const int which = []() { const char* e = getenv("VDA_SA_KERNEL"); return e ? atoi(e) : VDA_SA_DEFAULT_KERNEL; }();
+    if (which == 4) return sa4_launch(qkv, out, frames, N, heads, dtype, static_cast<cudaStream_t>(stream));
+  }
   // qkv is [frames, N, 3, heads, 64]: a 4-D tensor (d, which*heads + head, token, frame); token rows beyond N are
   // zero-filled by TMA instead of running into the next frame
   CUtensorMap tm;

@@ -418,7 +418,8 @@ constexpr uint32_t kIdescBMnMajor = 1u << 16;   // instruction-descriptor bit: B
 // host helpers shared by the TMA-fed kernels (defined in gemm.cu)
 int make_tensor_map(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims,
                     const cuuint64_t* strides_bytes, const cuuint32_t* box);
-constexpr int kTmapF32 = 100;   // `dtype` of make_tensor_map for fp32 tensors (epilogue residual / output tiles)
+constexpr int kTmapF32 = 100;          // `dtype` of make_tensor_map for fp32 tensors (epilogue residual / output tiles)
+constexpr int kTmapSwizzle64 = 1 << 10;  // OR-ed into `dtype`: SWIZZLE_64B instead of SWIZZLE_128B (boxes with 64-byte rows)
 int sm_count();        // SM count of the CURRENT device (cached per device)
 int current_device();  // cudaGetDevice, -1 on error
 

@@ -111,9 +111,139 @@ __global__ void eval_metric_finalize_kernel(const double* __restrict__ partials,
   for (int k = 0; k < 3; ++k) out[k] = kept > 0 ? acc[k] / kept : 0.0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Temporal alignment error (benchmark/eval/eval_tae.py:60-107 `tae_torch`, driven by eval_TAE :109-213): the aligned
+// depth of frame s is un-projected with the intrinsics, moved to frame d by the relative pose, projected back, rounded
+// to pixel indices and SCATTERED into an empty map of frame d (`depth_proj[valid_Y, valid_X] = valid_Z`); the error is
+// the masked mean of |depth_d - depth_proj| / depth_d over pixels where both are positive.
+// The scatter has duplicates: several source pixels land on one target pixel.  The reference's assignment keeps the
+// LAST writer in source order (NumPy / single-threaded index_put semantics), so the winner of a target pixel is the
+// source pixel with the largest flat index: pass 1 takes atomicMax of the source index per target pixel (integer,
+// order-independent, exact), pass 2 recomputes the winner's projected depth and reduces in a fixed order.
+// All arithmetic in double like the reference (float64 tensors); one job = one ordered (source, target) frame pair.
+// params per job: [0..8] R (row-major), [9..11] t, [12..15] fx, fy, cx, cy.
+// ---------------------------------------------------------------------------------------------
+struct TaePoint { long long ix, iy; double z; bool ok; };
+__device__ __forceinline__ TaePoint tae_project(const double* __restrict__ prm, double depth, int x, int y, int W, int H) {
+  const double fx = prm[12], fy = prm[13], cx = prm[14], cy = prm[15];
+  // eval_tae.py:72-75   X = (xx - cx) * depth1 / fx
+  const double X = (static_cast<double>(x) - cx) * depth / fx;
+  const double Y = (static_cast<double>(y) - cy) * depth / fy;
+  const double Z = depth;
+  // :80   points3d @ R.T + T
+  const double xw = X * prm[0] + Y * prm[1] + Z * prm[2] + prm[9];
+  const double yw = X * prm[3] + Y * prm[4] + Z * prm[5] + prm[10];
+  const double zw = X * prm[6] + Y * prm[7] + Z * prm[8] + prm[11];
+  // :83-88   project, round half to even (torch.round), to integer
+  const double xp = rint(xw * fx / zw + cx);
+  const double yp = rint(yw * fy / zw + cy);
+  TaePoint r;
+  r.z = zw;
+  r.ok = xp >= 0.0 && xp < static_cast<double>(W) && yp >= 0.0 && yp < static_cast<double>(H);   // false for NaN / inf
+  r.ix = r.ok ? static_cast<long long>(xp) : 0;
+  r.iy = r.ok ? static_cast<long long>(yp) : 0;
+  return r;
+}
+
+__global__ void __launch_bounds__(EV_THREADS)
+tae_scatter_kernel(const double* __restrict__ depth, const double* __restrict__ params, const int* __restrict__ src_idx,
+                   int H, int W, int* __restrict__ winners) {
+  const int job = blockIdx.y;
+  const long long hw = static_cast<long long>(H) * W;
+  const double* d = depth + static_cast<long long>(src_idx[job]) * hw;
+  const double* prm = params + static_cast<size_t>(job) * 16;
+  int* win = winners + static_cast<long long>(job) * hw;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<long long>(y) * W);
+    const TaePoint pt = tae_project(prm, d[i], x, y, W, H);
+    if (pt.ok) atomicMax(win + pt.iy * W + pt.ix, static_cast<int>(i));
+  }
+}
+
+// partials[job][block][2] = (sum |depth_d - proj| / depth_d, n) over the valid target pixels
+__global__ void __launch_bounds__(EV_THREADS)
+tae_error_kernel(const double* __restrict__ depth, const uint8_t* __restrict__ masks, const double* __restrict__ params,
+                 const int* __restrict__ src_idx, const int* __restrict__ dst_idx, int H, int W,
+                 const int* __restrict__ winners, double* __restrict__ partials) {
+  const int job = blockIdx.y;
+  const long long hw = static_cast<long long>(H) * W;
+  const double* ds = depth + static_cast<long long>(src_idx[job]) * hw;
+  const double* dd = depth + static_cast<long long>(dst_idx[job]) * hw;
+  const uint8_t* mk = masks ? masks + static_cast<long long>(dst_idx[job]) * hw : nullptr;
+  const double* prm = params + static_cast<size_t>(job) * 16;
+  const int* win = winners + static_cast<long long>(job) * hw;
+  double s[2] = {0, 0};
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = win[i];
+    if (w < 0) continue;                                   // depth_proj stays 0 here (:95)
+    const int y = w / W, x = w - y * W;
+    const double proj = tae_project(prm, ds[w], x, y, W, H).z;
+    const double g = dd[i];
+    if (proj > 0.0 && g > 0.0 && (!mk || mk[i])) {         // :103
+      s[0] += fabs(g - proj) / g;                          // compute_errors_torch(gt = depth2, pred = depth_proj)
+      s[1] += 1.0;
+    }
+  }
+  block_reduce_store<2>(s, partials + (static_cast<size_t>(job) * gridDim.x + blockIdx.x) * 2);
+}
+
+__global__ void tae_finalize_kernel(const double* __restrict__ partials, int jobs, int slabs, double* __restrict__ out) {
+  const int job = blockIdx.x * blockDim.x + threadIdx.x;
+  if (job >= jobs) return;
+  double s0 = 0, s1 = 0;
+  for (int b = 0; b < slabs; ++b) {
+    s0 += partials[(static_cast<size_t>(job) * slabs + b) * 2];
+    s1 += partials[(static_cast<size_t>(job) * slabs + b) * 2 + 1];
+  }
+  out[job] = s1 > 0.0 ? s0 / s1 : 0.0;                     // `return 0` when nothing is valid (:91-92, :104-105)
+}
+
+// aligned depth of the whole sequence (eval_tae.py:152-160): clip(1 / clip(scale * clip(pred, 1e-3) + shift, 1e-3), 1e-3, max)
+__global__ void __launch_bounds__(EV_THREADS)
+eval_aligned_depth_kernel(const float* __restrict__ pred, const double* __restrict__ ss, double max_depth, long long n,
+                          double* __restrict__ out) {
+  const double scale = ss[0], shift = ss[1];
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double a = fmax(scale * fmax(static_cast<double>(pred[i]), 1e-3) + shift, 1e-3);
+    out[i] = fmin(fmax(1.0 / a, 1e-3), max_depth);
+  }
+}
+
 }  // namespace vda
 
 using namespace vda;
+
+extern "C" int vda_eval_aligned_depth(const float* pred, const double* scale_shift, double max_depth, int64_t n, double* out,
+                                      void* stream) {
+  VDA_CHECK(n > 0 && max_depth > 0, "aligned depth: bad arguments");
+  long long g = (n + EV_THREADS - 1) / EV_THREADS;
+  if (g > 148 * 16) g = 148 * 16;
+  eval_aligned_depth_kernel<<<static_cast<unsigned>(g), EV_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred, scale_shift, max_depth, n, out);
+  VDA_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int vda_eval_tae(const double* depth, const uint8_t* masks, const double* params, const int32_t* src_idx,
+                            const int32_t* dst_idx, int jobs, int H, int W, int32_t* winners, double* partials, double* out,
+                            void* stream) {
+  VDA_CHECK(jobs > 0 && H > 0 && W > 0 && static_cast<long long>(H) * W < (1ll << 31), "tae: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long hw = static_cast<long long>(H) * W;
+  int slabs = static_cast<int>((hw + EV_THREADS - 1) / EV_THREADS);
+  if (slabs > VDA_EVAL_SLABS) slabs = VDA_EVAL_SLABS;
+  VDA_CUDA(cudaMemsetAsync(winners, 0xFF, static_cast<size_t>(jobs) * hw * sizeof(int32_t), st));   // -1: no writer
+  int sg = static_cast<int>((hw + EV_THREADS - 1) / EV_THREADS);
+  if (sg > 148 * 8) sg = 148 * 8;
+  tae_scatter_kernel<<<dim3(sg, jobs), EV_THREADS, 0, st>>>(depth, params, src_idx, H, W, winners);
+  tae_error_kernel<<<dim3(slabs, jobs), EV_THREADS, 0, st>>>(depth, masks, params, src_idx, dst_idx, H, W, winners, partials);
+  tae_finalize_kernel<<<(jobs + 63) / 64, 64, 0, st>>>(partials, jobs, slabs, out);
+  VDA_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int vda_eval_sequence(const float* pred, const void* gt, int gt_f64, int frames, int64_t hw, double max_depth,
                                  double* out, double* scale_shift, double* scratch, void* stream) {

@@ -60,6 +60,8 @@ struct GemmDev {
   const float* ln_c1;       // SPEC 5/6: c1[n] = sum_k W'[n,k]  (W' = 16-bit(LayerNorm weight * W))
   int stat_parts, stat_cols;
   float ln_eps, ln_inv_d;
+  int epi_nbuf;             // SPEC 4: residual boxes per epilogue warp (1 | 2)
+  uint32_t epi_warp_bytes;  // SPEC 4: shared memory per epilogue warp
   int pair;     // host only: launch the cta_group::2 variant
   int prefetch_max_kb;   // residual L2 prefetch of the next tile only when the K loop has at most this many blocks
 };
@@ -147,7 +149,7 @@ constexpr uint32_t kStagingBytes = kEpiWarps * kStageTile;
 template <typename T, int EPI, bool CONV, bool STAGED, int SPEC, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, const GemmDev p) {
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t rfull_bar[kEpiWarps][2];   // SPEC 4: residual chunk landed (per epilogue warp)
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -175,6 +177,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     if (SPEC == 4) {
       tma_prefetch_desc(&tmC);
+      if (p.out16) tma_prefetch_desc(&tmD);
       for (int w = 0; w < kEpiWarps; ++w) { mbar_init(&rfull_bar[w][0], 1); mbar_init(&rfull_bar[w][1], 1); }
     }
     mbar_fence_init();
@@ -315,21 +318,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int r = q * 32 + lane;
         const int nch32 = p.block_n >> 6;                       // 32-column chunks per warp (block_n % 64 == 0)
         const int c_begin = eh * (p.block_n >> 1);
-        const uint32_t buf0 = smem_base + p.stages * p.stage_bytes + ew * 8192u;
+        // per warp: epi_nbuf residual / result boxes (4 KB each) + one 2 KB box for the 16-bit copy.  epi_nbuf = 2 for
+        // short K loops (the epilogue is the critical path: chunk k+2 is requested while chunk k+1 is processed), 1 for
+        // long ones (fc2, K = 4096: the MMAs of a tile take 4x longer than its epilogue, the operand ring needs the
+        // shared memory more)
+        const uint32_t nbuf = static_cast<uint32_t>(p.epi_nbuf);
+        const uint32_t buf0 = smem_base + p.stages * p.stage_bytes + ew * p.epi_warp_bytes;
+        const uint32_t hbuf = buf0 + nbuf * 4096u;
         uint64_t* rfull = rfull_bar[ew];
-        // flat chunk k of this warp: tile tile0 + (k / nch32) * tile_step, chunk k % nch32; buffer k & 1
+        // flat chunk k of this warp: tile tile0 + (k / nch32) * tile_step, chunk k % nch32; buffer k % nbuf
         auto issue_load = [&](uint32_t k) {
           const int tl = tile0 + static_cast<int>(k / nch32) * tile_step;
           if (tl >= p.num_tiles) return;
           const int ci = static_cast<int>(k % nch32);
           const int nb = tl % p.tiles_n;
           const int mb = CTA2 ? 2 * (tl / p.tiles_n) + rank : tl / p.tiles_n;
-          mbar_arrive_expect_tx(&rfull[k & 1u], 4096u);
-          tma_load_2d(reinterpret_cast<void*>(smem_gen + (buf0 - smem_base) + (k & 1u) * 4096u), &tmC, &rfull[k & 1u],
+          const uint32_t b = k % nbuf;
+          mbar_arrive_expect_tx(&rfull[b], 4096u);
+          tma_load_2d(reinterpret_cast<void*>(smem_gen + (buf0 - smem_base) + b * 4096u), &tmC, &rfull[b],
                       nb * p.block_n + c_begin + ci * 32, mb * BLOCK_M + q * 32);
         };
-        if (tile == tile0) {                                    // first tile of this CTA: prime both buffers
-          if (elect_one()) { issue_load(0); issue_load(1); }
+        if (tile == tile0) {                                    // first tile of this CTA: prime the buffer(s)
+          if (elect_one()) { issue_load(0); if (nbuf > 1) issue_load(1); }
           __syncwarp();
         }
         const uint32_t kbase = static_cast<uint32_t>((tile - tile0) / tile_step) * nch32;
@@ -339,10 +349,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float shift = 0.f;
         for (int ci = 0; ci < nch32; ++ci) {
           const uint32_t k = kbase + ci;
-          const uint32_t buf = buf0 + (k & 1u) * 4096u;
+          const uint32_t buf = buf0 + (k % nbuf) * 4096u;
           const int c0 = c_begin + ci * 32;
           const int col = col_base + c0;
-          mbar_wait(&rfull[k & 1u], (k >> 1) & 1u);
+          mbar_wait(&rfull[k % nbuf], (k / nbuf) & 1u);
           if (ci == 0) {
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
@@ -371,18 +381,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             h16[2 * j] = H16<T>::pack2(v.a.x, v.a.y);
             h16[2 * j + 1] = H16<T>::pack2(v.b.x, v.b.y);
           }
-          if (p.out16 && row_ok) {
-            uint4* o16 = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out16) + grow * p.ldo + col);
+          if (p.out16) {
+            // 32 rows x 64 B box, SWIZZLE_64B: 16-byte slot j of row r sits at slot j ^ ((r >> 1) & 3)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o16[j] = make_uint4(h16[4 * j], h16[4 * j + 1], h16[4 * j + 2], h16[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              sts128(hbuf + static_cast<uint32_t>(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)), h16[4 * j], h16[4 * j + 1],
+                     h16[4 * j + 2], h16[4 * j + 3]);
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
             tma_store_2d(&tmC, reinterpret_cast<const void*>(smem_gen + (buf - smem_base)), col, m_blk * BLOCK_M + q * 32);
+            if (p.out16)
+              tma_store_2d(&tmD, reinterpret_cast<const void*>(smem_gen + (hbuf - smem_base)), col, m_blk * BLOCK_M + q * 32);
             bulk_commit();
-            bulk_wait_read<0>();          // the store has read the buffer: it may receive the residual of chunk k + 2
-            issue_load(k + 2);
+            bulk_wait_read<0>();          // the stores have read their boxes: the next residual chunk may land
+            issue_load(k + nbuf);
           }
           __syncwarp();
         }
@@ -884,11 +898,14 @@ int make_tensor_map(CUtensorMap* m, int dtype, const void* base, int rank, const
   PFN_encodeTiled enc = get_encode();
   VDA_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const bool sw64 = (dtype & kTmapSwizzle64) != 0;
+  dtype &= ~kTmapSwizzle64;
   const CUtensorMapDataType cdt = dtype == kTmapF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                   : (dtype == VDA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
   CUresult r = enc(m, cdt,
                    static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims, strides_bytes, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VDA_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu box %u %u)",
             static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
@@ -942,8 +959,8 @@ static int pick_block_n(int N, int tiles_m) {
 }
 
 template <typename T, int EPI, bool CONV, bool STAGED, int SPEC, bool CTA2>
-static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmDev& d, size_t smem,
-                   cudaStream_t st) {
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmD,
+                   const GemmDev& d, size_t smem, cudaStream_t st) {
   auto kfn = gemm_kernel<T, EPI, CONV, STAGED, SPEC, CTA2>;
   VDA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(kfn), smem));   // per (kernel, device)
   const bool pdl = pdl_enabled();
@@ -973,15 +990,15 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  VDA_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, tmC, d));
+  VDA_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, tmC, tmD, d));
   VDA_CUDA(cudaGetLastError());
   return 0;
 }
-struct Maps { CUtensorMap a, b, c; };   // c: fp32 residual / output tile map (SPEC 4 only; else a copy of a)
+struct Maps { CUtensorMap a, b, c, d; };   // c / d: fp32 residual-output and 16-bit copy tile maps (SPEC 4 only; else copies of a)
 template <typename T, int EPI, bool CONV, bool STAGED, int SPEC = 0>
 static int launch(const Maps& tm, const GemmDev& d, size_t smem, cudaStream_t st) {
-  if (d.pair) return launch2<T, EPI, CONV, STAGED, SPEC, true>(tm.a, tm.b, tm.c, d, smem, st);
-  return launch2<T, EPI, CONV, STAGED, SPEC, false>(tm.a, tm.b, tm.c, d, smem, st);
+  if (d.pair) return launch2<T, EPI, CONV, STAGED, SPEC, true>(tm.a, tm.b, tm.c, tm.d, d, smem, st);
+  return launch2<T, EPI, CONV, STAGED, SPEC, false>(tm.a, tm.b, tm.c, tm.d, d, smem, st);
 }
 
 template <typename T>
@@ -1149,7 +1166,9 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
   VDA_CHECK(spec == 4 || (!p->out16 && !p->row_stats_out), "out16 / row_stats_out: unsupported epilogue combination");
   VDA_CHECK((spec == 5 || spec == 6) == (p->row_stats_in != nullptr), "row_stats_in: unsupported epilogue combination");
   // epilogue staging: 8 transposition tiles of 4 KB, or (SPEC 4) 8 x 2 TMA boxes of 4 KB
-  const uint32_t staging = spec == 4 ? kEpiWarps * 8192u : (d.staged ? kStagingBytes : 0u);
+  d.epi_nbuf = d.num_k_blocks >= 32 ? 1 : 2;
+  d.epi_warp_bytes = static_cast<uint32_t>(d.epi_nbuf) * 4096u + (p->out16 ? 2048u : 0u);
+  const uint32_t staging = spec == 4 ? kEpiWarps * d.epi_warp_bytes : (d.staged ? kStagingBytes : 0u);
   int stages = static_cast<int>((227u * 1024u - 1024u - 512u - staging) / d.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   d.stages = stages;
@@ -1167,11 +1186,17 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
   d.tail_w = p->tail_w; d.tail_b = p->tail_b;
 
   tm.c = tm.a;
+  tm.d = tm.a;
   if (spec == 4) {
     cuuint64_t dims[2] = {(cuuint64_t)p->N, (cuuint64_t)p->M};
     cuuint64_t strides[1] = {(cuuint64_t)p->ldo * 4};
     cuuint32_t box[2] = {32, 32};
     if (make_tensor_map(&tm.c, kTmapF32, p->out, 2, dims, strides, box)) return 1;
+    if (p->out16) {
+      VDA_CHECK((reinterpret_cast<uintptr_t>(p->out16) & 15) == 0, "out16 must be 16-byte aligned");
+      cuuint64_t strides16[1] = {(cuuint64_t)p->ldo * 2};
+      if (make_tensor_map(&tm.d, p->dtype | kTmapSwizzle64, p->out16, 2, dims, strides16, box)) return 1;
+    }
     d.out16 = p->out16;
     d.stats_out = reinterpret_cast<float2*>(p->row_stats_out);
     d.stat_parts = 2 * d.tiles_n;
