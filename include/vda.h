@@ -92,6 +92,12 @@ typedef struct vda_gemm_params {
   const float* ln_c1;
   int32_t stat_parts, stat_cols;
   float ln_eps;
+
+  /* Validation precision (`fp32=True`, reference video_depth.py:203-205): weights as a hi | lo pair of h16 matrices.
+   * a_k > 0: A is [M, a_k] and Wt is [N, K] with K == 2 * round_up(a_k, 64): columns [0, a_k) hold h16(W), columns
+   * [K/2, K/2 + a_k) hold h16(W - h16(W)), the rest zeros; A is walked twice, so out = A (Wh + Wl)^T with the weights'
+   * rounding error squared.  0: plain (A is [M, K]). */
+  int32_t a_k;
 } vda_gemm_params;
 
 int vda_version(void);

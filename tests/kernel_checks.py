@@ -136,6 +136,39 @@ def check_gemm_ln_fold(M, N, K, dt, act=ACT_NONE, seed=0, offset=0.3):
     return _err(out, ref), _tol(ref, dt) * (2.0 + abs(offset))
 
 
+def check_gemm_split(M, N, K, dt, conv=None, seed=0):
+    """Validation precision: weights as a hi | lo pair of 16-bit matrices (ops.split_hi_lo, vda_gemm_params.a_k), A walked
+    twice.  Against the fp32 product with the UNROUNDED weights: only A's rounding is left, so the error must be well
+    below the plain 16-bit-weight GEMM's on the same data.  conv=(n,H,W,C): the implicit 3x3 conv walks its taps twice."""
+    g = torch.Generator().manual_seed(seed)
+    if conv is None:
+        a = _rand((M, K), seed, 1.0, dt)
+        w32 = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+        ref = a.float() @ w32.t()
+        out_s = torch.empty(M, N, device=DEV, dtype=torch.float32)
+        out_p = torch.empty(M, N, device=DEV, dtype=torch.float32)
+        ops.gemm(a, ops.split_hi_lo(w32, dt), out_s)
+        ops.gemm(a, w32.to(dt).contiguous(), out_p)
+    else:
+        n, H, W, Ci = conv
+        from video_depth_anything_b200.engine import pack_conv3x3
+        x = _rand((n, Ci, H, W), seed, 1.0, dt)
+        w4 = (torch.randn(N, Ci, 3, 3, generator=g) / math.sqrt(9 * Ci)).to(DEV)
+        ref = F.conv2d(x.float(), w4, None, padding=1).permute(0, 2, 3, 1).reshape(n * H * W, N)
+        a = x.permute(0, 2, 3, 1).contiguous()
+        wp = pack_conv3x3(w4, Ci, N)
+        out_s = torch.empty(n * H * W, N, device=DEV, dtype=torch.float32)
+        out_p = torch.empty(n * H * W, N, device=DEV, dtype=torch.float32)
+        ops.gemm(a, ops.split_hi_lo(wp, dt), out_s, conv_shape=(n, H, W, Ci))
+        ops.gemm(a, wp.to(dt).contiguous(), out_p, conv_shape=(n, H, W, Ci))
+    torch.cuda.synchronize()
+    e_s, e_p = _err(out_s, ref), _err(out_p, ref)
+    rms_s = (out_s - ref).pow(2).mean().sqrt().item()
+    rms_p = (out_p - ref).pow(2).mean().sqrt().item()
+    assert rms_s < 0.85 * rms_p, f"hi|lo weights do not reduce the error: rms {rms_s:.3e} vs plain {rms_p:.3e}"
+    return e_s, _tol(ref, dt)
+
+
 def check_gemm_patch_rowmap(dt, frames=3, P=20, N=384, K=592, seed=0):
     """row_group remap used by the patch-embed GEMM: out row = m + m/P + 1, res1 row = m%P + 1."""
     M = frames * P
@@ -535,6 +568,10 @@ CHECKS = [
     ("gemm 30140x1152x384 fp16 LN fold", lambda: check_gemm_ln_fold(30140, 1152, 384, HF)),
     ("gemm 30140x1536x384 fp16 LN fold + gelu, mean=3", lambda: check_gemm_ln_fold(30140, 1536, 384, HF, act=ACT_GELU, offset=3.0)),
     ("gemm 2740x1024x4096 bf16 ls+res f32 separate out (SPEC 3)", lambda: check_gemm_plain(2740, 1024, 4096, BF, gamma=True, res1="f32", out_f32=True, inplace=False)),
+    ("gemm hi|lo weights 2740x1024x1024 fp16", lambda: check_gemm_split(2740, 1024, 1024, HF)),
+    ("gemm hi|lo weights 1000x384x592 fp16 (K tail)", lambda: check_gemm_split(1000, 384, 592, HF)),
+    ("gemm hi|lo weights 3000x256x256 bf16", lambda: check_gemm_split(3000, 256, 256, BF)),
+    ("conv3x3 hi|lo weights 2x37x37 256->256 fp16", lambda: check_gemm_split(0, 256, 0, HF, conv=(2, 37, 37, 256))),
     ("gemm K tail 592 bf16", lambda: check_gemm_plain(500, 384, 592, BF)),
     ("gemm K=24 bf16 (single partial k-block)", lambda: check_gemm_plain(500, 64, 24, BF)),
     ("gemm patch-embed row map bf16", lambda: check_gemm_patch_rowmap(BF)),

@@ -41,15 +41,15 @@ def test_gemm_params_struct_layout():
     from video_depth_anything_b200._lib import GemmParams
     src = ('#include "vda.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu", sizeof(vda_gemm_params), '
            '__builtin_offsetof(vda_gemm_params, out), __builtin_offsetof(vda_gemm_params, tail_b));'
-           'printf(" %zu %zu", __builtin_offsetof(vda_gemm_params, out16), __builtin_offsetof(vda_gemm_params, ln_eps));return 0;}')
+           'printf(" %zu %zu", __builtin_offsetof(vda_gemm_params, out16), __builtin_offsetof(vda_gemm_params, a_k));return 0;}')
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "p.c"), "-o",
                                os.path.join(d, "p")])
-        size, off_out, off_tb, off_o16, off_eps = map(int, subprocess.check_output([os.path.join(d, "p")]).split())
+        size, off_out, off_tb, off_o16, off_ak = map(int, subprocess.check_output([os.path.join(d, "p")]).split())
     assert ctypes.sizeof(GemmParams) == size
     assert GemmParams.out.offset == off_out and GemmParams.tail_b.offset == off_tb
-    assert GemmParams.out16.offset == off_o16 and GemmParams.ln_eps.offset == off_eps
+    assert GemmParams.out16.offset == off_o16 and GemmParams.a_k.offset == off_ak
 
 
 def test_no_cpu_fallback():

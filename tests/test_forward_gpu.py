@@ -15,21 +15,14 @@ pytestmark = pytest.mark.gpu
 from e2e_checks import GOLD, build_model, golden_case, stage_report  # noqa: E402
 from oracle import vda_oracle as O  # noqa: E402
 
-TOL = 1e-2
-# bf16 operands carry 8 mantissa bits (fp16, the reference's autocast type: 11).  With fp32 accumulation, residual
-# streams and statistics the bf16 engine stays within 1e-2 at p99.9 everywhere, but the single worst pixel of a
-# 518x518 map lands at ~1.0-1.3e-2 (DESIGN.md "Numerics"); PyTorch's own bf16 autocast of the reference is at
-# 1.4e-2..3.1e-2 on the same harness.  fp16 mode meets 1e-2 on the max with ~10x margin.
-TOL_BF16_MAX = 2e-2
+TOL = 1e-2           # north_star: per-pixel relative depth error, every advertised dtype, on the MAX (no percentile escape)
+TOL_VALIDATION = 1e-3   # north_star: fp32-accumulate validation mode (`fp32=True`)
 
 
 def _check(dtype, mx, p999, mean, what):
     msg = f"{what} {dtype}: rel err max {mx:.3e} p99.9 {p999:.3e} mean {mean:.3e}"
     print(msg)
-    if dtype == torch.float16:
-        assert mx <= TOL, msg
-    else:
-        assert p999 <= TOL and mx <= TOL_BF16_MAX, msg
+    assert mx <= TOL, msg
 MAN = json.load(open(os.path.join(GOLD, "MANIFEST.json")))["cases"]
 FWD = [k for k, v in MAN.items() if v["kind"] == "forward"]
 IVD = [k for k, v in MAN.items() if v["kind"] == "infer_video_depth"]
@@ -97,11 +90,24 @@ def test_full_size_window_vs_oracle(enc, dtype, tol):
     fin, rows, d, ref = stage_report(enc, 0, (1, 32, 3, 518, 518), 1234, dtype, oracle_device="cuda")
     assert (ref > 0).float().mean() > 0.99
     _check(dtype, *fin, f"{enc} 1x32x518x518")
-    if enc == "vitl" and dtype == torch.float16:
-        # north_star's validation bar: <= 1e-3 against the fp32 reference with fp32 accumulation.  fp16 operands +
-        # fp32 accumulators / residual stream / statistics is that mode here (8.9e-4 on the headline window; the
-        # forward is bit-reproducible, so this is not a flaky margin)
-        assert fin[0] <= 1e-3, fin
+
+
+@pytest.mark.parametrize("enc", ["vitl", "vits"])
+def test_validation_mode_full_size_window(enc):
+    """north_star's validation bar: <= 1e-3 per pixel against the fp32 reference in an fp32-accumulate mode.  `fp32=True`
+    (reference video_depth.py:203-205: autocast off) selects the validation engine -- fp16 activations, hi | lo fp16
+    weight pairs, fp32 accumulation / residuals / statistics -- from a model whose own dtype is bf16."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m, sd = build_model(enc, 0, torch.bfloat16)
+    x = torch.randn(1, 32, 3, 518, 518, generator=torch.Generator().manual_seed(1234))
+    d = m.forward(x.cuda(), fp32=True).float().cpu()
+    ref = O.forward({k: v.cuda() for k, v in sd.items()}, x.cuda(), enc).float().cpu()
+    mx, p999, mean = O.rel_err(d, ref)
+    print(f"{enc} 1x32x518x518 validation mode: rel err max {mx:.3e} p99.9 {p999:.3e} mean {mean:.3e}")
+    assert mx <= TOL_VALIDATION, (mx, p999, mean)
+    fast = m.forward(x.cuda()).float().cpu()                 # the fast path is a different engine, same weights
+    assert O.rel_err(fast, ref)[0] <= TOL
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["fp16", "bf16"])

@@ -33,6 +33,7 @@ class GemmParams(C.Structure):
         ("tail_w", C.c_void_p), ("tail_b", C.c_float),
         ("out16", C.c_void_p), ("row_stats_out", C.c_void_p), ("row_stats_in", C.c_void_p), ("ln_c1", C.c_void_p),
         ("stat_parts", C.c_int32), ("stat_cols", C.c_int32), ("ln_eps", C.c_float),
+        ("a_k", C.c_int32),
     ]
 
 

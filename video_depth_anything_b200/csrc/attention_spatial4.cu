@@ -7,19 +7,24 @@
 // stalls (`wait`) 30 %, MUFU queue / result stalls 15 %: with two warps the scheduler has nothing else to issue.
 // Restructuring waits inside that design (own MMA issuer per stream, split-KV items) changed nothing (0.386 -> 0.390 ms).
 //
-// Here a CTA (768 threads, one per SM) runs FOUR streams, each = one MMA-issuing warp + one softmax warpgroup owning a
-// 128-query tile, on 64-key score tiles:
+// Here a CTA (640 threads, one per SM) runs FOUR streams, each = one softmax warpgroup owning a 128-query tile and
+// issuing its own MMAs, on 64-key score tiles:
 //   warp 0        TMA producer: per item the Q tiles of up to four neighbouring query tiles of one (frame, head), then the
 //                 K / V tiles (64 keys x 64) of that (frame, head) through two 5-slot rings shared by all four streams
-//   warps 1-4     tcgen05.mma issuer of stream 0-3:  S = Q K^T (SS, 128 x 64 x 64), then per step  O += P V  (TS: P from
-//                 TMEM, V from smem as MN-major operand)  immediately followed by the next S
-//   warps 5-7     idle (register donors)
-//   warps 8-23    softmax warpgroups of streams 0-3: one thread per query row, the 64 scores of a row go TMEM ->
-//                 registers, online softmax (lazy rescale), P packed to 16 bit and written back INTO the S columns
+//   warp 1        TMEM allocation;  warps 2-3 idle (the control warpgroup donates its registers)
+//   warps 4-19    softmax warpgroups of streams 0-3: one thread per query row, the 64 scores of a row go TMEM ->
+//                 registers, online softmax (lazy rescale), P packed to 16 bit and written back INTO the S columns.
+//                 The first warp of a warpgroup is also the stream's tcgen05.mma issuer (one elected lane):
+//                 S = Q K^T (SS, 128 x 64 x 64), then per step  O += P V  (TS: P from TMEM, V from smem as MN-major
+//                 operand)  immediately followed by the next S.  (A stream is strictly serial -- scores, softmax, P V, next
+//                 scores -- so a separate issuer warp would only add a hand-over; and with 768 threads the register
+//                 pool released by the control warps -- setmaxnreg can only draw on registers of the same CTA -- tops
+//                 out at 104 per softmax thread, 640 threads allow 112.)
 // TMEM (512 columns): stream t owns S_t = columns [64 t, 64 t + 64) and O_t = [256 + 64 t, ...); P_t aliases S_t[0, 32).
 // Because the issuer queues O += P V and the next S back to back (the tensor pipe executes one thread's MMAs in order),
-// a stream needs only two barriers per step (s_ready: issuer -> warpgroup, p_ready: warpgroup -> issuer): no s_free, no
-// o_done, and "S(j+1) is complete" implies "O += P(j) V(j) is complete", which is all the lazy rescale needs.
+// a stream needs one mbarrier (s_ready: tensor pipe -> warpgroup) and one 128-thread named barrier (all P stores done ->
+// issuer) per step: no s_free, no o_done, and "S(j+1) is complete" implies "O += P(j) V(j) is complete", which is all the
+// lazy rescale needs.
 // A stream idles while its own MMAs run (~2 x 128 tensor cycles + latency); the other three fill the issue slots: four
 // softmax warps per scheduler instead of two, 64 + 32 live score registers per thread instead of 128 + 32.
 // Ring slots / Q buffers expect four arrivals (one tcgen05.commit per consuming stream); for a query-tile group with
@@ -35,8 +40,8 @@ constexpr int BN = 64;             // keys per tile
 constexpr int D = 64;              // head dim
 constexpr int NS = 4;              // streams
 constexpr int KS = 5, VS = 5;      // K / V ring depth
-constexpr int THREADS = 768;       // 8 control warps + 4 softmax warpgroups
-constexpr int REGS_CTRL = 32, REGS_SOFTMAX = 112;   // 256*32 + 512*112 = 65536
+constexpr int THREADS = 640;       // 4 control warps + 4 softmax warpgroups
+constexpr int REGS_CTRL = 24, REGS_SOFTMAX = 112;   // 128*24 + 512*112 = 60416 <= 640 * 96 (the launch allocation)
 constexpr uint32_t Q_BYTES = BM * D * 2;      // 16 KB
 constexpr uint32_t KV_BYTES = BN * D * 2;     // 8 KB
 constexpr uint32_t SMEM_BYTES = 2 * NS * Q_BYTES + (KS + VS) * KV_BYTES + 1024;
@@ -94,7 +99,7 @@ spatial_attention4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Sa4Pa
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full[2], q_empty[2];
   __shared__ __align__(8) uint64_t k_full[KS], k_empty[KS], v_full[VS], v_empty[VS];
-  __shared__ __align__(8) uint64_t s_ready[NS], p_ready[NS], o_ready[NS];
+  __shared__ __align__(8) uint64_t s_ready[NS], o_ready[NS];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
@@ -113,7 +118,6 @@ spatial_attention4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Sa4Pa
     for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], NS); }
     for (int t = 0; t < NS; ++t) {
       mbar_init(&s_ready[t], 1);
-      mbar_init(&p_ready[t], 128);
       mbar_init(&o_ready[t], 1);
     }
     mbar_fence_init();
@@ -134,7 +138,7 @@ spatial_attention4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Sa4Pa
     nact = min(NS, p.n_qt - tile0);
   };
 
-  if (warp < 8) {
+  if (warp < 4) {
     sa4_reg_dec<REGS_CTRL>();
     if (warp == 0 && lane == 0) {
       // ===================================== TMA producer =====================================
@@ -165,82 +169,71 @@ spatial_attention4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Sa4Pa
           if (++vs == VS) { vs = 0; vph ^= 1u; }
         }
       }
-    } else if (warp >= 1 && warp <= NS) {
-      // ===================================== MMA issuer of stream t ============================
-      // warp-uniform control flow, one elected lane issues the tcgen05 instructions
-      const int t = warp - 1;
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0;
-      uint32_t n_pv = 0;                                   // P V tiles issued by this stream (p_ready parity)
-      const uint32_t idesc_pv = umma_idesc(H16<T>::kUmmaFmt, D) | kIdescBMnMajor;
-      const uint32_t tS = tmem_base + COL_S + t * BN, tO = tmem_base + COL_O + t * D;
-      for (int i = 0; i < n_my; ++i) {
-        int frame, head, tile0, nact;
-        decode(static_cast<int>(blockIdx.x) + i * stride, frame, head, tile0, nact);
-        if (t >= nact) {                                   // no query tile for this stream: only count the ring uses
-          const int k2 = ks + p.n_kv, v2 = vs + p.n_kv;
-          kph ^= static_cast<uint32_t>(k2 / KS) & 1u;  ks = k2 % KS;
-          vph ^= static_cast<uint32_t>(v2 / VS) & 1u;  vs = v2 % VS;
-          continue;
-        }
-        const int qb = i & 1;
-        const uint64_t da = umma_desc_sw128(smem_base + offQ + (qb * NS + t) * Q_BYTES);
-        mbar_wait(&q_full[qb], (i >> 1) & 1u);
-        auto issue_s = [&](int j) {
-          const uint32_t idesc = umma_idesc(H16<T>::kUmmaFmt, static_cast<uint32_t>(sa4_kv_cols(p, j)));
-          mbar_wait(&k_full[ks], kph);
-          tc_fence_after();
-          const uint64_t db = umma_desc_sw128(smem_base + offK + ks * KV_BYTES);
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < D / 16; ++k) umma_f16(tS, da + 2u * k, db + 2u * k, idesc, k);
-            umma_commit(&s_ready[t]);
-            umma_commit(&k_empty[ks]);
-            if (j == p.n_kv - 1) umma_commit(&q_empty[qb]);     // last S of the item: Q is free once these retire
-          }
-          __syncwarp();
-          if (++ks == KS) { ks = 0; kph ^= 1u; }
-        };
-        issue_s(0);
-        for (int j = 0; j < p.n_kv; ++j) {
-          // O += P(j) V(j)
-          const int nk = sa4_kv_cols(p, j) >> 4;
-          mbar_wait(&v_full[vs], vph);
-          mbar_wait(&p_ready[t], n_pv & 1u);
-          tc_fence_after();
-          const uint64_t db = umma_desc_sw128_mn(smem_base + offV + vs * KV_BYTES);
-          if (elect_one()) {
-            for (int k = 0; k < nk; ++k)    // 16 keys per MMA: 8 TMEM columns of P, 16 rows (2048 B) of V
-              umma_f16_ts(tO, tS + 8u * k, db + 128u * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&v_empty[vs]);
-            if (j == p.n_kv - 1) umma_commit(&o_ready[t]);
-          }
-          __syncwarp();
-          ++n_pv;
-          if (++vs == VS) { vs = 0; vph ^= 1u; }
-          // the next S overwrites S / P: queued behind the P V MMAs above (same issuing thread: executed in order)
-          if (j + 1 < p.n_kv) issue_s(j + 1);
-        }
-      }
     }
   } else {
-    // ===================================== softmax warpgroups ===============================
+    // ===================================== softmax warpgroups (+ MMA issue) ==================
     sa4_reg_inc<REGS_SOFTMAX>();
-    const int t = (warp - 8) >> 2;                    // stream handled by this warpgroup
+    const int t = (warp - 4) >> 2;                    // stream handled by this warpgroup
     const int quad = warp & 3;                        // TMEM lane quadrant of this warp
+    const bool issuer = quad == 0;                    // first warp of the warpgroup issues the stream's MMAs
     const int row = quad * 32 + lane;                 // query row inside the tile
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_base + lane_base + COL_S + t * BN;
     const uint32_t tO = tmem_base + lane_base + COL_O + t * D;
+    const uint32_t tS0 = tmem_base + COL_S + t * BN, tO0 = tmem_base + COL_O + t * D;   // MMA operand addresses (lane 0)
     const float sc = 0.125f * 1.4426950408889634f;    // d^-0.5 * log2(e)
     const float2 sc2 = make_float2(sc, sc);
     uint32_t cnt = 0, n_done = 0;                     // key-tile steps / items finished by this stream
     T* outp = reinterpret_cast<T*>(p.out);
+    // issuer state: ring cursors of the S (K ring) and P V (V ring) issue streams; k_acc = items whose K uses are counted
+    int ks = 0, vs = 0, k_acc = 0, k_issued = -1;
+    uint32_t kph = 0, vph = 0;
+    const uint32_t idesc_pv = umma_idesc(H16<T>::kUmmaFmt, D) | kIdescBMnMajor;
+
+    auto item_active = [&](int i) {
+      int frame, head, tile0, nact;
+      decode(static_cast<int>(blockIdx.x) + i * stride, frame, head, tile0, nact);
+      return t < nact;
+    };
+    // S(i, j) of this stream (issuer warp only; warp-uniform, one elected lane issues)
+    auto issue_s = [&](int i, int j) {
+      const int qb = i & 1;
+      if (j == 0) {
+        for (; k_acc < i; ++k_acc) {                  // items in between have no tile for this stream: count their uses
+          const int k2 = ks + p.n_kv;
+          kph ^= static_cast<uint32_t>(k2 / KS) & 1u;
+          ks = k2 % KS;
+        }
+        mbar_wait(&q_full[qb], (i >> 1) & 1u);
+        k_issued = i;
+      }
+      const uint32_t idesc = umma_idesc(H16<T>::kUmmaFmt, static_cast<uint32_t>(sa4_kv_cols(p, j)));
+      const uint64_t da = umma_desc_sw128(smem_base + offQ + (qb * NS + t) * Q_BYTES);
+      mbar_wait(&k_full[ks], kph);
+      tc_fence_after();
+      const uint64_t db = umma_desc_sw128(smem_base + offK + ks * KV_BYTES);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) umma_f16(tS0, da + 2u * k, db + 2u * k, idesc, k);
+        umma_commit(&s_ready[t]);
+        umma_commit(&k_empty[ks]);
+        if (j == p.n_kv - 1) umma_commit(&q_empty[qb]);     // last S of the item: Q is free once these retire
+      }
+      __syncwarp();
+      if (++ks == KS) { ks = 0; kph ^= 1u; }
+      if (j == p.n_kv - 1) k_acc = i + 1;
+    };
 
     for (int i = 0; i < n_my; ++i) {
       int frame, head, tile0, nact;
       decode(static_cast<int>(blockIdx.x) + i * stride, frame, head, tile0, nact);
-      if (t >= nact) continue;
+      if (t >= nact) {                                 // no query tile for this stream: only count the V ring uses
+        const int v2 = vs + p.n_kv;
+        vph ^= static_cast<uint32_t>(v2 / VS) & 1u;
+        vs = v2 % VS;
+        continue;
+      }
+      if (issuer && k_issued != i) issue_s(i, 0);      // (normally issued ahead, at the end of the previous item)
       float m_run = 0.f, l_run = 0.f;
       for (int j = 0; j < p.n_kv; ++j, ++cnt) {
         const int cols = sa4_kv_cols(p, j);
@@ -317,7 +310,30 @@ spatial_attention4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Sa4Pa
         l_run += (la.x + la.y) + (lb.x + lb.y);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_ready[t]);
+        named_bar_sync(1 + t, 128);                   // every row of P(j) is in TMEM
+        if (issuer) {
+          // O += P(j) V(j), then the next S right behind it (same issuing thread: executed in order, so the S / P
+          // columns are overwritten only after P V has read them)
+          tc_fence_after();
+          const int nk = cols >> 4;
+          mbar_wait(&v_full[vs], vph);
+          const uint64_t db = umma_desc_sw128_mn(smem_base + offV + vs * KV_BYTES);
+          if (elect_one()) {
+            for (int k = 0; k < nk; ++k)    // 16 keys per MMA: 8 TMEM columns of P, 16 rows (2048 B) of V
+              umma_f16_ts(tO0, tS0 + 8u * k, db + 128u * k, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&v_empty[vs]);
+            if (j == p.n_kv - 1) umma_commit(&o_ready[t]);
+          }
+          __syncwarp();
+          if (++vs == VS) { vs = 0; vph ^= 1u; }
+          if (j + 1 < p.n_kv) {
+            issue_s(i, j + 1);
+          } else {                                     // first S of this stream's next item (Q is double-buffered)
+            int i2 = i + 1;
+            while (i2 < n_my && !item_active(i2)) ++i2;
+            if (i2 < n_my) issue_s(i2, 0);
+          }
+        }
       }
       // ---- epilogue: O / l -> 16 bit -> global ----
       mbar_wait(&o_ready[t], n_done & 1u);
@@ -343,7 +359,7 @@ spatial_attention4_kernel(const __grid_constant__ CUtensorMap tmQKV, const Sa4Pa
           }
         }
       }
-      tc_fence_before();   // the O reads above are ordered before this thread's next p_ready arrive
+      tc_fence_before();   // the O reads above are ordered before the next item's first P V (behind the next named barrier)
     }
   }
 
@@ -372,6 +388,16 @@ int sa4_launch(const void* qkv, void* out, int frames, int N, int heads, int dty
   p.n_kv = (N + sa4::BN - 1) / sa4::BN;
   p.out = out;
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+  {
+    // setmaxnreg.inc can only draw on registers this CTA was launched with: a smaller launch allocation than planned
+    // would leave the softmax warpgroups waiting for registers forever -- refuse instead
+    cudaFuncAttributes fa;
+    VDA_CUDA(cudaFuncGetAttributes(&fa, dtype == VDA_BF16 ? reinterpret_cast<const void*>(spatial_attention4_kernel<__nv_bfloat16>)
+                                                         : reinterpret_cast<const void*>(spatial_attention4_kernel<__half>)));
+    VDA_CHECK(fa.numRegs * sa4::THREADS >= 128 * sa4::REGS_CTRL + 512 * sa4::REGS_SOFTMAX,
+              "attention4: launch allocation of %d registers/thread cannot feed setmaxnreg %d/%d", fa.numRegs, sa4::REGS_CTRL,
+              sa4::REGS_SOFTMAX);
+  }
   if (dtype == VDA_BF16) {
     auto k = spatial_attention4_kernel<__nv_bfloat16>;
     VDA_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(k), sa4::SMEM_BYTES));

@@ -60,6 +60,7 @@ struct GemmDev {
   const float* ln_c1;       // SPEC 5/6: c1[n] = sum_k W'[n,k]  (W' = 16-bit(LayerNorm weight * W))
   int stat_parts, stat_cols;
   float ln_eps, ln_inv_d;
+  int a_k_blocks;           // k-blocks of A (== num_k_blocks unless the weights are a hi | lo pair: A is then walked twice)
   int epi_nbuf;             // SPEC 4: residual boxes per epilogue warp (1 | 2)
   uint32_t epi_warp_bytes;  // SPEC 4: shared memory per epilogue warp
   int pair;     // host only: launch the cta_group::2 variant
@@ -229,7 +230,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int dy = tap / 3 - 1, dx = tap % 3 - 1;
               tma_load_4d_pair(sA, &tmA, &full_bar[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
             } else {
-              tma_load_2d_pair(sA, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+              tma_load_2d_pair(sA, &tmA, &full_bar[stage], (kb % p.a_k_blocks) * BLOCK_K, m_blk * BLOCK_M);
             }
             tma_load_2d_pair(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * p.block_n + rank * (p.block_n >> 1));
           } else {
@@ -238,13 +239,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int dy = tap / 3 - 1, dx = tap % 3 - 1;
               tma_load_4d(sA, &tmA, &full_bar[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
             } else {
-              tma_load_2d(sA, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+              tma_load_2d(sA, &tmA, &full_bar[stage], (kb % p.a_k_blocks) * BLOCK_K, m_blk * BLOCK_M);
             }
             tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * p.block_n);
           }
         }
         __syncwarp();
-        if (CONV && ++cb == p.cblocks) { cb = 0; ++tap; }
+        if (CONV && ++cb == p.cblocks) { cb = 0; if (++tap == 9) tap = 0; }   // (hi | lo weights: the taps are walked twice)
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -1081,8 +1082,14 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
   CUtensorMap& tmA = tm.a;
   CUtensorMap& tmB = tm.b;
 
+  // Weights as a hi | lo pair of 16-bit matrices (validation precision): Wt is [N, 2 * Ka'] with Ka' = a_k rounded up to a
+  // k-block, the second half holding the 16-bit rounding residue of the first; A ([M, a_k]) is walked twice.
+  const int a_k = p->a_k > 0 ? p->a_k : p->K;
+  const int a_kp = (a_k + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+  VDA_CHECK(p->a_k <= 0 || p->K == 2 * a_kp, "hi|lo weights: K (%d) must be 2 * round_up(a_k = %d, 64)", p->K, p->a_k);
+  d.a_k_blocks = a_kp / BLOCK_K;
   if (conv) {
-    VDA_CHECK(p->C % 64 == 0 && p->K == 9 * p->C, "conv mode needs C %% 64 == 0 and K == 9*C (C=%d K=%d)", p->C, p->K);
+    VDA_CHECK(p->C % 64 == 0 && a_k == 9 * p->C, "conv mode needs C %% 64 == 0 and K == 9*C (C=%d K=%d)", p->C, a_k);
     VDA_CHECK(p->M == p->n_img * p->H * p->W, "conv mode: M must be n_img*H*W");
     d.H = p->H; d.W = p->W;
     // pick the 128-pixel box shape (bw x bh) wasting the fewest out-of-image pixels
@@ -1101,9 +1108,9 @@ extern "C" int vda_gemm(const vda_gemm_params* p, void* stream) {
     cuuint32_t box[4] = {64, (cuuint32_t)d.bw, (cuuint32_t)d.bh, 1};
     if (make_tensor_map(&tmA, p->dtype, p->A, 4, dims, strides, box)) return 1;
   } else {
-    VDA_CHECK(p->lda >= p->K && p->lda % 8 == 0, "lda (%lld) must be >= K and a multiple of 8", (long long)p->lda);
+    VDA_CHECK(p->lda >= a_k && p->lda % 8 == 0, "lda (%lld) must be >= K and a multiple of 8", (long long)p->lda);
     d.tiles_m = (p->M + BLOCK_M - 1) / BLOCK_M;
-    cuuint64_t dims[2] = {(cuuint64_t)p->K, (cuuint64_t)p->M};
+    cuuint64_t dims[2] = {(cuuint64_t)a_k, (cuuint64_t)p->M};
     cuuint64_t strides[1] = {(cuuint64_t)p->lda * 2};
     cuuint32_t box[2] = {64, 128};
     if (make_tensor_map(&tmA, p->dtype, p->A, 2, dims, strides, box)) return 1;

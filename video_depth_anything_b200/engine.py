@@ -67,7 +67,7 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor, half: int):
 
 class Engine:
     def __init__(self, encoder: str, features: int, out_channels: List[int], dtype=torch.bfloat16,
-                 device="cuda", num_frames: int = 32):
+                 device="cuda", num_frames: int = 32, weight_split: bool = False):
         if encoder not in ENCODER_DIMS:
             raise ValueError(f"unknown encoder {encoder!r}")
         self.encoder = encoder
@@ -86,6 +86,12 @@ class Engine:
         # stream and per-row statistics; qkv / fc1 apply mean / rstd in their epilogues): removes 2 of the 2.04 LayerNorm
         # launches per block.  VDA_LN_FOLD=0: the standalone LayerNorm kernel everywhere.
         self.ln_fold = os.environ.get("VDA_LN_FOLD", "1") != "0"
+        # Validation precision (`fp32=True`): every GEMM / conv weight is a hi | lo pair of 16-bit matrices (22 mantissa
+        # bits; the GEMM walks A twice), activations stay 16-bit with fp32 accumulation / residuals / statistics.  Twice the
+        # tensor work; the LayerNorm fold is off (one rounding less on the normalised rows).
+        self.weight_split = weight_split
+        if weight_split:
+            self.ln_fold = False
         self.device = torch.device(device)
         self.num_frames = num_frames
         self.w: Dict[str, torch.Tensor] = {}
@@ -114,8 +120,11 @@ class Engine:
         def f32(k):
             return sd[k].detach().to(dev, torch.float32).contiguous()
 
+        split = self.weight_split
+
         def h16(t):
-            return t.to(dev, torch.float32).to(dt).contiguous()
+            t = t.to(dev, torch.float32)
+            return ops.split_hi_lo(t.reshape(t.shape[0], -1), dt) if split else t.to(dt).contiguous()
 
         def fold_ln(wk, bk, nk):
             """(h16(g * W), c1 = row sums of the ROUNDED folded matrix, c2 = W beta + b) for y = LN(x) W^T + b."""
@@ -148,7 +157,8 @@ class Engine:
         hdt = self.hdtype
 
         def h16(t):                                    # head weights: head operand type  # noqa: F811
-            return t.to(dev, torch.float32).to(hdt).contiguous()
+            t = t.to(dev, torch.float32)
+            return ops.split_hi_lo(t.reshape(t.shape[0], -1), hdt) if split else t.to(hdt).contiguous()
         for i in range(4):
             w[f"proj{i}.w"] = h16(sd[f"{h}projects.{i}.weight"].reshape(oc[i], D))
             w[f"proj{i}.b"] = f32(f"{h}projects.{i}.bias")
@@ -174,7 +184,8 @@ class Engine:
         b = torch.zeros(self.c_oc1, device=dev)
         b[:F // 2] = sd[h + "scratch.output_conv1.bias"].to(dev, torch.float32)
         w["oc1.b"] = b
-        w["oc2.w"] = h16(pack_conv3x3(sd[h + "scratch.output_conv2.0.weight"].to(dev, torch.float32), self.c_oc1, 32))
+        w["oc2.w"] = pack_conv3x3(sd[h + "scratch.output_conv2.0.weight"].to(dev, torch.float32), self.c_oc1, 32) \
+            .to(hdt).contiguous()                      # (the fused tail kernel reads it directly: always a plain matrix)
         w["oc2.b"] = f32(h + "scratch.output_conv2.0.bias")
         w["oc3.w"] = f32(h + "scratch.output_conv2.2.weight").reshape(32)
         self.oc3_b = float(sd[h + "scratch.output_conv2.2.bias"].reshape(-1)[0])

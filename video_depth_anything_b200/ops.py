@@ -42,6 +42,19 @@ def _count(n=1):
     LAUNCHES += n
 
 
+def split_hi_lo(w: torch.Tensor, dtype) -> torch.Tensor:
+    """fp32 weight matrix [N, K] -> h16 [N, 2 * round_up(K, 64)] = [h16(W) | h16(W - h16(W))] (zero padded): the operand
+    format of the validation-precision GEMMs (vda_gemm_params.a_k)."""
+    N, K = w.shape
+    kp = (K + 63) // 64 * 64
+    hi = w.to(dtype)
+    lo = (w - hi.float()).to(dtype)
+    out = torch.zeros(N, 2 * kp, dtype=dtype, device=w.device)
+    out[:, :K] = hi
+    out[:, kp:kp + K] = lo
+    return out
+
+
 def rowstat_layout(M: int, N: int):
     """(parts, part_cols) of the per-row partial statistics a residual GEMM with `row_stats` writes for an [M, N] output."""
     lib = _lib.load()
@@ -67,11 +80,15 @@ def gemm(a: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, bias=None, gam
         assert a.is_contiguous() and a.numel() == n * H * W * Cc
         p.a_mode, p.n_img, p.H, p.W, p.C = A_CONV3, n, H, W, Cc
         p.M, p.lda = n * H * W, Cc
+        ka = 9 * Cc
     else:
         assert a.dim() == 2 and a.stride(1) == 1
         p.a_mode = A_PLAIN
         p.M, p.lda = (a.shape[0] if M is None else M), a.stride(0)
-        assert a.shape[1] == K, (a.shape, wt.shape)
+        ka = a.shape[1]
+    if K != ka:      # weights packed as a hi | lo pair (split_hi_lo): A is walked twice
+        assert K == 2 * ((ka + 63) // 64 * 64), (a.shape, wt.shape)
+        p.a_k = ka
     p.A, p.Wt = _p(a), _p(wt)
     p.bias, p.gamma, p.act = _p(bias), _p(gamma), act
     if res1 is not None:
@@ -116,7 +133,7 @@ def gemm(a: torch.Tensor, wt: torch.Tensor, out: torch.Tensor, *, bias=None, gam
         p.stat_cols = K // p.stat_parts
     if PROFILE is not None:
         _INFO.update(kind=("conv3x3" if conv_shape is not None else "gemm") + f"/epi{epilogue}",
-                     M=int(p.M), N=int(N), K=int(K), flops=2.0 * p.M * N * K)
+                     M=int(p.M), N=int(N), K=int(ka), flops=2.0 * p.M * N * ka)
     check(lib.vda_gemm(C.byref(p), _stream()))
     _count()
     return out

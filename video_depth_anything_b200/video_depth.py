@@ -87,18 +87,19 @@ class VideoDepthAnything(nn.Module):
         return self.to("cuda" if device is None else device)
 
     def _ensure_engine(self, validation: bool = False) -> Engine:
-        """The engine of the model's dtype; `validation=True`: the high-precision engine behind `fp32=True` (fp16
-        operands -- 11 mantissa bits instead of bf16's 8 -- with fp32 accumulation, residual streams, statistics and
-        softmax; built lazily, holds its own packed copy of the weights)."""
+        """The engine of the model's dtype; `validation=True`: the high-precision engine behind `fp32=True`: fp16
+        activations (11 mantissa bits instead of bf16's 8), every weight matrix as a hi | lo pair of fp16 matrices (22
+        bits; the GEMMs walk A twice), fp32 accumulation, residual streams, statistics and softmax.  Built lazily, holds
+        its own packed copy of the weights, about twice the tensor work of the fast path."""
         if self._device.type != "cuda":
             raise RuntimeError("VideoDepthAnything (B200 engine) has no CPU path: call .to('cuda') first")
-        if validation and self.dtype != VALIDATION_DTYPE:
+        if validation:
             if self._engine_val is None or self._engine_val.device != self._device:
                 from . import _lib
                 _lib.load()
                 with torch.cuda.device(self._device):
                     self._engine_val = Engine(self.encoder, self.features, self.out_channels, VALIDATION_DTYPE,
-                                              self._device, self.num_frames)
+                                              self._device, self.num_frames, weight_split=True)
                     self._engine_val.load(self._sd)
             return self._engine_val
         if self._engine is None or self._engine.device != self._device:
@@ -130,9 +131,9 @@ class VideoDepthAnything(nn.Module):
         least squares, clamp and cross-fade.  Frames are uploaded in chunks through pinned staging buffers while
         earlier windows compute, finished depth frames stream back the same way; the host never touches a pixel.
         `fp32=True` (the reference disables autocast, video_depth.py:203-205 / benchmark/infer/infer.py:58) selects the
-        validation-precision engine: fp16 tensor-core operands with fp32 accumulation, residual streams, statistics and
-        softmax (<= 1e-3 of the fp32 reference on the full ViT-L window, tests/test_forward_gpu.py), whatever the
-        model's own dtype; there is no fp32-operand tensor path on this engine, and the flag is not silently ignored.
+        validation-precision engine: fp16 activations, weights as hi | lo fp16 pairs, fp32 accumulation, residual streams,
+        statistics and softmax (<= 1e-3 of the fp32 reference on full vitl AND vits windows, tests/test_forward_gpu.py),
+        whatever the model's own dtype; the flag is not silently ignored.
         `window_ids` / `raw_only` are the multi-GPU hooks (parallel.py): compute only those windows and return
         the raw, resized per-window depths [len(window_ids),32,H0,W0] on the device, skipping alignment; with
         `aligner` the windows are pushed into that WindowAligner instead (the caller finishes it) and None is returned.
