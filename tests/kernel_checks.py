@@ -17,6 +17,10 @@ from video_depth_anything_b200 import ops
 from video_depth_anything_b200._lib import ACT_GELU, ACT_NONE, ACT_RELU, EPI_CONVT, EPI_GEGLU, EPI_LINEAR, EPI_TAIL
 
 DEV = "cuda"
+# the references are plain fp32 ops: no TF32 anywhere (cuDNN convolutions use it by default, which rounds the weights to
+# 10 mantissa bits -- exactly what a 16-bit-weight kernel does, so a TF32 reference would hide weight-rounding error)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def _rand(shape, seed, scale=1.0, dtype=torch.float32):
