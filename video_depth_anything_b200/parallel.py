@@ -190,6 +190,7 @@ def two_phase_finalise(raws: torch.Tensor, counts: Sequence[int], K: int, n: int
             halo = torch.empty(INTERP_LEN, h0, w0, dtype=torch.float32, device=dev)
             reqs.append(dist.P2POp(dist.irecv, halo, owners[i - 1], group))
     works = dist.batch_isend_irecv(reqs) if reqs else []
+    stamp("halo posted")
     # ---- 2. anchors (slots 0, 1, 12) of every window on every rank ----
     kmax = max(counts)
     mine = torch.zeros(kmax, 3, h0, w0, dtype=torch.float32, device=dev)
@@ -205,11 +206,13 @@ def two_phase_finalise(raws: torch.Tensor, counts: Sequence[int], K: int, n: int
         anchors = gathered.view(world * kmax, 3, h0, w0)
     else:
         anchors = torch.cat([gathered[r, :counts[r]] for r in range(world)])                  # [K,3,h0,w0]
+    stamp("anchors gathered")
     # ---- 3. (scale, shift) of every window: the whole recurrence in one cooperative kernel ----
     table = kern.align_chain(anchors, affine)                                                  # video_depth.py:227-250
     stamp("scale/shift table")
     for w in works:
         w.wait()
+    stamp("halo received")
     # ---- 4. my frames: same kernel sequence as WindowAligner.push with the tabulated (scale, shift), in place in
     #      the raw stack (the kernels are elementwise): window j's slots 2..9 are cross-faded with the aligned slots
     #      24..31 of window j-1, slots 10..31 are aligned; its slots [2, 24) are then final video frames
@@ -289,13 +292,20 @@ def _infer_two_phase(model, frames, target_fps, input_size, device, group):
             share = len(os.sched_getaffinity(0))
         except AttributeError:
             share = (os.cpu_count() or 8) // world
-        drain = HostDrain(host, dev, touch=slice(lo, hi), copy_threads=max(2, min(6, share - 1)), touch_threads=1)
+        direct = os.environ.get("VDA_DIRECT_D2H", "1") != "0"      # GPU writes into the page-locked result rows
+        drain = HostDrain(host, dev, touch=slice(lo, hi), copy_threads=max(2, min(6, share - 1)), touch_threads=1,
+                          direct=direct)
         raws = model.infer_video_depth(frames, target_fps, input_size=input_size, device=dev,
                                        window_ids=list(parts[rank]), raw_only=True)          # [k_r,32,h0,w0]
         stamp("windows computed")
         two_phase_finalise(raws, counts, K, n, not model.metric, _DeviceKernels(dev), drain.send, group, stamp)
         drain.finish()
         stamp("downloaded")
+        if trace:
+            print(f"video trace rank {rank}: drain copied {drain.copied_bytes / 1e6:.0f} MB in {drain.copy_seconds * 1e3:.0f} ms "
+                  f"of copy-thread time ({drain.COPY_THREADS} threads), waited {drain.touch_wait_seconds * 1e3:.0f} ms for the "
+                  f"page touch, {drain.event_wait_seconds * 1e3:.0f} ms for D2H events; direct D2H "
+                  f"{'on' if drain.direct and drain._reg_ok else 'off'}", flush=True)
     dist.barrier(group=group)
     stamp("barrier")
     if trace:
