@@ -365,7 +365,9 @@ def main():
         base = np.random.default_rng(0).integers(0, 256, (64, H, Wd, 3), dtype=np.uint8)
         frames = base[np.arange(args.video_frames) % 64]
         # (measured scaling of this arm, 2048 frames: 1 GPU 3.9 s, 2 GPUs 2.10 s, 8 GPUs 0.64 s)
-        infer_video_depth_sharded(model, frames[:66 * world], 24, device=dev)      # warm-up: graphs for 32/22-frame encodes
+        # warm-up on the same video: graphs for the 32/22-frame encodes, allocator blocks, pinned staging / NCCL buffers of
+        # the sizes the timed call uses (a short warm-up video left an unexplained ~25 ms in the 8-GPU exchange)
+        infer_video_depth_sharded(model, frames, 24, device=dev)
         barrier()
         l0 = ops.LAUNCHES
         t0 = time.perf_counter()

@@ -3,7 +3,7 @@
 cd "$GRAFT_REPO_ROOT"
 O=gpurun_out
 nvidia-smi -L | wc -l
-VDA_TRACE_VIDEO=1 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 10 --warmup 3 > $O/c7_bench8.json 2> $O/c7_bench8.err; echo "bench8 rc=$?"
+VDA_TRACE_VIDEO=1 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 6 --warmup 3 --no-other-configs --no-e2e > $O/c7_bench8.json 2> $O/c7_bench8.err; echo "bench8 rc=$?"
 grep -E "video trace" $O/c7_bench8.json $O/c7_bench8.err | tail -8 | cut -c1-260
 python - <<'PY'
 import json

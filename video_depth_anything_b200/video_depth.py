@@ -395,6 +395,9 @@ class HostDrain:
 
         def work():
             try:
+                # not right away: cudaHostUnregister holds the context lock for tens of ms (measured: a dist.barrier
+                # issued right behind it waited 36 ms), and the caller's next CUDA calls come now
+                time.sleep(0.5)
                 torch.cuda.cudart().cudaHostUnregister(ptr)
             finally:
                 del keep_ref[:]
