@@ -305,7 +305,7 @@ def _infer_two_phase(model, frames, target_fps, input_size, device, group):
             print(f"video trace rank {rank}: drain copied {drain.copied_bytes / 1e6:.0f} MB in {drain.copy_seconds * 1e3:.0f} ms "
                   f"of copy-thread time ({drain.COPY_THREADS} threads), waited {drain.touch_wait_seconds * 1e3:.0f} ms for the "
                   f"page touch, {drain.event_wait_seconds * 1e3:.0f} ms for D2H events; direct D2H "
-                  f"{'on' if drain.direct and drain._reg_ok else 'off'}", flush=True)
+                  f"{'on' if drain.direct and drain._reg_ok else 'off'} ({drain._reg_note})", flush=True)
     dist.barrier(group=group)
     stamp("barrier")
     if trace:

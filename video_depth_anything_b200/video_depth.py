@@ -237,6 +237,8 @@ class FeatureCache:
 
 _PINNED: dict = {}
 _PINNED_LOCK = threading.Lock()
+_REGISTERED: list = []             # (address, owner array) of result regions page-locked by HostDrain(direct=True)
+_REGISTERED_LOCK = threading.Lock()
 
 
 def _pinned_acquire(key, count: int, shape, dtype):
@@ -340,7 +342,7 @@ class HostDrain:
         leave in the tail: the staging -> result copies of all ranks share the host's memory bandwidth (measured: 2.2 GB in
         ~55 ms whatever the rank count).  Falls back to the staged path if the registration fails."""
         self.host, self.device = host, device
-        self.direct, self._reg_ok, self._reg_done = direct, False, threading.Event()
+        self.direct, self._reg_ok, self._reg_done, self._reg_note = direct, False, threading.Event(), ""
         self._reg_slice = touch if touch is not None else slice(0, host.shape[0])
         if direct:
             threading.Thread(target=self._register, daemon=True).start()
@@ -377,32 +379,40 @@ class HostDrain:
     def _register(self) -> None:
         try:
             time.sleep(0.05)
+            rt = torch.cuda.cudart()
+            # page locks of earlier calls are released here, in the background of THIS call (cudaHostUnregister holds the
+            # context lock for tens of ms: done right after a call it delayed the caller's next CUDA call, e.g. a barrier)
+            with _REGISTERED_LOCK:
+                stale, _REGISTERED[:] = list(_REGISTERED), []
+            for ptr, _keep in stale:
+                rt.cudaHostUnregister(ptr)
             region = self.host[self._reg_slice]
             if region.size:
-                rc = int(torch.cuda.cudart().cudaHostRegister(region.ctypes.data, region.nbytes, 0))
+                ptr = region.ctypes.data
+                rc = int(rt.cudaHostRegister(ptr, region.nbytes, 0))
+                if rc == 712:                    # cudaErrorHostMemoryAlreadyRegistered: a stale entry for this address range
+                    rt.cudaHostUnregister(ptr)
+                    rc = int(rt.cudaHostRegister(ptr, region.nbytes, 0))
+                self._reg_note = f"cudaHostRegister rc={rc}"
                 if rc == 0:
                     self._host_t = torch.from_numpy(region)
                     self._reg_ok = True
-        except Exception:                        # noqa: BLE001  (no registration: staged copies)
+                    with _REGISTERED_LOCK:
+                        _REGISTERED.append((ptr, self.host))     # keeps the mapping alive while it is page-locked
+        except Exception as exc:                 # noqa: BLE001  (no registration: staged copies)
             self._reg_ok = False
+            self._reg_note = f"{type(exc).__name__}: {exc}"
         finally:
+            if not self._reg_ok:
+                # staged path after all: get its pinned buffers and fault the result pages in now, in the background,
+                # not in the tail (first-touch page faults divide the copy bandwidth by 5)
+                try:
+                    self.stage, self._stage_token = _pinned_acquire(("drain",) + self._stage_shape[1:], self.STAGES,
+                                                                    self._stage_shape, torch.float32)
+                    self.host[self._reg_slice].reshape(-1)[::1024].fill(0)
+                except Exception:                # noqa: BLE001
+                    pass
             self._reg_done.set()
-
-    def _unregister_later(self) -> None:
-        """Release the page lock in the background (the data is already in place; cudaHostUnregister is slow)."""
-        region = self.host[self._reg_slice]
-        ptr, keep = region.ctypes.data, self.host
-
-        def work():
-            try:
-                # not right away: cudaHostUnregister holds the context lock for tens of ms (measured: a dist.barrier
-                # issued right behind it waited 36 ms), and the caller's next CUDA calls come now
-                time.sleep(0.5)
-                torch.cuda.cudart().cudaHostUnregister(ptr)
-            finally:
-                del keep_ref[:]
-        keep_ref = [keep]
-        threading.Thread(target=work, daemon=True).start()
 
     def _drain_loop(self) -> None:
         while True:
@@ -470,8 +480,7 @@ class HostDrain:
         if self.direct:
             self._reg_done.wait()
             if self._reg_ok:
-                self.copy_stream.synchronize()
-                self._unregister_later()
+                self.copy_stream.synchronize()   # (the page lock is released by the next call's registration thread)
         self.jobs.put(None)
         self.jobs.join()
         self.drainer.join()
