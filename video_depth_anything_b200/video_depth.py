@@ -237,8 +237,6 @@ class FeatureCache:
 
 _PINNED: dict = {}
 _PINNED_LOCK = threading.Lock()
-_REGISTERED: list = []             # (address, owner array) of result regions page-locked by HostDrain(direct=True)
-_REGISTERED_LOCK = threading.Lock()
 
 
 def _pinned_acquire(key, count: int, shape, dtype):
@@ -378,14 +376,9 @@ class HostDrain:
 
     def _register(self) -> None:
         try:
+            torch.cuda.set_device(self.device)   # a new thread starts on device 0: register in THIS rank's context
             time.sleep(0.05)
             rt = torch.cuda.cudart()
-            # page locks of earlier calls are released here, in the background of THIS call (cudaHostUnregister holds the
-            # context lock for tens of ms: done right after a call it delayed the caller's next CUDA call, e.g. a barrier)
-            with _REGISTERED_LOCK:
-                stale, _REGISTERED[:] = list(_REGISTERED), []
-            for ptr, _keep in stale:
-                rt.cudaHostUnregister(ptr)
             region = self.host[self._reg_slice]
             if region.size:
                 ptr = region.ctypes.data
@@ -397,8 +390,6 @@ class HostDrain:
                 if rc == 0:
                     self._host_t = torch.from_numpy(region)
                     self._reg_ok = True
-                    with _REGISTERED_LOCK:
-                        _REGISTERED.append((ptr, self.host))     # keeps the mapping alive while it is page-locked
         except Exception as exc:                 # noqa: BLE001  (no registration: staged copies)
             self._reg_ok = False
             self._reg_note = f"{type(exc).__name__}: {exc}"
@@ -413,6 +404,23 @@ class HostDrain:
                 except Exception:                # noqa: BLE001
                     pass
             self._reg_done.set()
+
+    def _unregister_later(self) -> None:
+        """Release the page lock in the background, half a second from now: the data is in place, but
+        cudaHostUnregister holds the context lock for tens of ms per 100 MB -- right behind finish() it delayed the
+        caller's next CUDA call (a dist.barrier waited 36 ms), and run back to back with the next call's registration it
+        stalled that call's launches by 0.5 s.  The array (and with it the mapping) is kept alive until then."""
+        region = self.host[self._reg_slice]
+        ptr, keep_ref, dev = region.ctypes.data, [self.host], self.device
+
+        def work():
+            try:
+                torch.cuda.set_device(dev)
+                time.sleep(0.5)
+                torch.cuda.cudart().cudaHostUnregister(ptr)
+            finally:
+                del keep_ref[:]
+        threading.Thread(target=work, daemon=True).start()
 
     def _drain_loop(self) -> None:
         while True:
@@ -480,7 +488,8 @@ class HostDrain:
         if self.direct:
             self._reg_done.wait()
             if self._reg_ok:
-                self.copy_stream.synchronize()   # (the page lock is released by the next call's registration thread)
+                self.copy_stream.synchronize()
+                self._unregister_later()
         self.jobs.put(None)
         self.jobs.join()
         self.drainer.join()
