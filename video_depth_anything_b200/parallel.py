@@ -311,12 +311,10 @@ def _infer_two_phase(model, frames, target_fps, input_size, device, group):
     if trace:
         print(f"video trace rank {rank}: " + ", ".join(f"{a} +{(t - stamps[0][1]) * 1e3:.0f} ms" for a, t in stamps[1:]), flush=True)
     if rank != 0:
-        del host, drain
-        try:
-            shm.close()
-        except BufferError:           # a view is still referenced somewhere: the mapping goes away with the process
-            pass
+        del host
+        drain.unregister_later(close_after=shm)   # page lock released in the background, THEN the attachment is closed
         return None, target_fps
+    drain.unregister_later()
     shm.unlink()                      # the name goes away now; the mapping lives as long as the returned array
     _LIVE_SEGMENTS.append(shm)
     return host, target_fps

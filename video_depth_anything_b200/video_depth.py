@@ -405,13 +405,24 @@ class HostDrain:
                     pass
             self._reg_done.set()
 
-    def _unregister_later(self) -> None:
+    def unregister_later(self, close_after=None) -> None:
         """Release the page lock in the background, half a second from now: the data is in place, but
         cudaHostUnregister holds the context lock for tens of ms per 100 MB -- right behind finish() it delayed the
         caller's next CUDA call (a dist.barrier waited 36 ms), and run back to back with the next call's registration it
-        stalled that call's launches by 0.5 s.  The array (and with it the mapping) is kept alive until then."""
+        stalled that call's launches by 0.5 s.  The array is kept alive until then, and `close_after` (the rank's
+        SharedMemory attachment) is closed only afterwards: NumPy does not hold a buffer export, so closing the mapping
+        while it is page-locked leaves a stale registration behind that the next mapping at the same address trips
+        over (cudaErrorHostMemoryAlreadyRegistered)."""
+        if not (self.direct and self._reg_ok):
+            if close_after is not None:
+                try:
+                    close_after.close()
+                except BufferError:
+                    pass
+            return
         region = self.host[self._reg_slice]
-        ptr, keep_ref, dev = region.ctypes.data, [self.host], self.device
+        ptr, keep_ref, dev = region.ctypes.data, [self.host, close_after], self.device
+        self.host = None
 
         def work():
             try:
@@ -419,7 +430,13 @@ class HostDrain:
                 time.sleep(0.5)
                 torch.cuda.cudart().cudaHostUnregister(ptr)
             finally:
+                shm = keep_ref[1]
                 del keep_ref[:]
+                if shm is not None:
+                    try:
+                        shm.close()
+                    except BufferError:
+                        pass
         threading.Thread(target=work, daemon=True).start()
 
     def _drain_loop(self) -> None:
@@ -488,8 +505,7 @@ class HostDrain:
         if self.direct:
             self._reg_done.wait()
             if self._reg_ok:
-                self.copy_stream.synchronize()
-                self._unregister_later()
+                self.copy_stream.synchronize()   # (the caller releases the page lock: unregister_later)
         self.jobs.put(None)
         self.jobs.join()
         self.drainer.join()
