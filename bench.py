@@ -270,10 +270,13 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if args.encoder == "vitl" and os.path.exists(tpath):
         t = json.load(open(tpath))
-        algo = {"proj": 43840 * 1024 * 2 + 1024 * 1024 * 2 + 2 * 43840 * 1024 * 4,
-                "fc1": 43840 * 1024 * 2 + 4096 * 1024 * 2 + 43840 * 4096 * 2,
-                "fc2": 43840 * 4096 * 2 + 4096 * 1024 * 2 + 2 * 43840 * 1024 * 4,
-                "qkv": 43840 * 1024 * 2 + 3072 * 1024 * 2 + 43840 * 3072 * 2}
+        # algorithmic bytes per launch with the LayerNorm fold: proj / fc2 also write the 16-bit copy of the rows and
+        # 8 (mean, M2) partials per row; qkv / fc1 read those partials
+        M_, st = 43840, 43840 * 8 * 8
+        algo = {"proj": M_ * 1024 * 2 + 1024 * 1024 * 2 + 2 * M_ * 1024 * 4 + M_ * 1024 * 2 + st,
+                "fc1": M_ * 1024 * 2 + 4096 * 1024 * 2 + M_ * 4096 * 2 + st,
+                "fc2": M_ * 4096 * 2 + 4096 * 1024 * 2 + 2 * M_ * 1024 * 4 + M_ * 1024 * 2 + st,
+                "qkv": M_ * 1024 * 2 + 3072 * 1024 * 2 + M_ * 3072 * 2 + st}
         det = {n: {"dram_bytes": t[f"gemm_prof.ncu-rep:{i}"]["dram_bytes"], "algorithmic_bytes": algo[n]}
                for i, n in enumerate(("proj", "fc1", "fc2", "qkv")) if f"gemm_prof.ncu-rep:{i}" in t}
         if len(det) == 4:

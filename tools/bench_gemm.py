@@ -63,6 +63,47 @@ def conv(name, n, H, W, ci, co, **kw):
     print(f"{name:34s} M={M:8d} N={co:5d} K={9 * ci:5d}  {ms * 1e3:8.1f} us  {2.0 * M * co * 9 * ci / ms / 1e9:7.1f} TF/s", flush=True)
 
 
+def fold_set(M=43840, D=1024, once=False):
+    """The four encoder GEMMs as the engine launches them with the LayerNorm fold: proj / fc2 with the 16-bit copy + row
+    statistics (SPEC 4), qkv / fc1 with the fold epilogue (SPEC 5 / 6).  `once`: one launch each (ncu)."""
+    parts, cols = ops.rowstat_layout(M, D)
+    tok = torch.randn(M, D, device="cuda")
+    x16 = torch.empty(M, D, device="cuda", dtype=DT)
+    stats = torch.empty(M, parts, 2, device="cuda")
+    ops.rowstats_cast(tok, x16, stats)
+    ones, bias_d = torch.ones(D, device="cuda"), torch.randn(D, device="cuda")
+
+    def run(name, fn, flops):
+        if once:
+            fn()
+            torch.cuda.synchronize()
+            return
+        ms = timeit(fn)
+        print(f"{name:44s} {ms * 1e3:8.1f} us  {flops / ms / 1e9:7.1f} TF/s", flush=True)
+
+    att = torch.randn(M, D, device="cuda").to(DT)
+    wp = (torch.randn(D, D, device="cuda") / D ** 0.5).to(DT)
+    run("proj + ls + residual + x16 + stats (SPEC 4)",
+        lambda: ops.gemm(att, wp, tok, bias=bias_d, gamma=ones, res1=tok, out16=x16, row_stats_out=stats), 2.0 * M * D * D)
+    w1 = (torch.randn(4 * D, D, device="cuda") / D ** 0.5).to(DT)
+    hid = torch.empty(M, 4 * D, device="cuda", dtype=DT)
+    c1, c2 = w1.float().sum(1).contiguous(), torch.randn(4 * D, device="cuda")
+    run("fc1 + GELU, LayerNorm folded (SPEC 6)",
+        lambda: ops.gemm(x16, w1, hid, bias=c2, act=ACT_GELU, ln_fold=(stats, c1, 1e-6)), 2.0 * M * 4 * D * D)
+    w2 = (torch.randn(D, 4 * D, device="cuda") / (4 * D) ** 0.5).to(DT)
+    run("fc2 + ls + residual + x16 + stats (SPEC 4)",
+        lambda: ops.gemm(hid, w2, tok, bias=bias_d, gamma=ones, res1=tok, out16=x16, row_stats_out=stats), 2.0 * M * 4 * D * D)
+    wq = (torch.randn(3 * D, D, device="cuda") / D ** 0.5).to(DT)
+    qkv = torch.empty(M, 3 * D, device="cuda", dtype=DT)
+    cq1, cq2 = wq.float().sum(1).contiguous(), torch.randn(3 * D, device="cuda")
+    run("qkv, LayerNorm folded (SPEC 5)",
+        lambda: ops.gemm(x16, wq, qkv, bias=cq2, ln_fold=(stats, cq1, 1e-6)), 2.0 * M * 3 * D * D)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] in ("fold", "foldprof"):
+    fold_set(once=sys.argv[1] == "foldprof")
+    sys.exit(0)
+
 if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("tail", "ln")):
     M = 43840
     if len(sys.argv) > 1 and sys.argv[1] == "prof":     # one launch per shape, for ncu
