@@ -239,6 +239,32 @@ int vda_align_chain(const float* anchors, int n_windows, int64_t hw, int affine,
 int vda_affine_clamp_blend(const float* x, const float* scale_shift, const float* prev, const float* blend_w,
                            float* out, int frames, int64_t hw, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Handle-level API: the whole forward of VideoDepthAnything (video_depth_anything/video_depth.py:36-164) behind five calls,
+ * for hosts that do not want to re-implement the engine's launch schedule (csrc/model.cu is that schedule: the same
+ * sequence of the operator entry points above as video_depth_anything_b200/engine.py, bit-identical output).
+ *
+ *   vda_create            encoder "vits" | "vitl" (dinov2.py:339-378), features / out_channels / num_frames as the reference
+ *                         constructor (video_depth.py:38-63); dtype = operand type of the encoder (the DPT head uses fp16)
+ *   vda_set_weight        one tensor of the reference state dict (same keys as model.state_dict()), fp32,
+ *                         HOST memory, row-major in the reference's own shape; copies
+ *   vda_finalize_weights  packs everything into the kernel layouts on `device` (strict: a missing key is an error)
+ *   vda_workspace_bytes   size of the scratch buffer vda_forward needs for a [B,T,3,H,W] input (-1 on error)
+ *   vda_forward           x: device fp32 [B,T,3,H,W] (normalised frames, as forward() receives them) -> depth: device fp32
+ *                         [B,T,H,W] >= 0.  workspace: device, 1024-byte aligned, >= vda_workspace_bytes.  Enqueues on
+ *                         `stream`, does not synchronise or allocate (the first call for a new token grid other than
+ *                         37x37 resamples the position embedding into model-owned memory).  H, W multiples of 14
+ *                         (patch_embed.py:73-74), T <= num_frames (dpt_temporal.py:38). */
+typedef struct vda_model vda_model;
+int vda_create(const char* encoder, int features, const int32_t* out_channels, int num_frames, int dtype, int device,
+               vda_model** out);
+int vda_set_weight(vda_model* m, const char* name, const float* host_data, const int64_t* shape, int ndim);
+int vda_finalize_weights(vda_model* m);
+int64_t vda_workspace_bytes(vda_model* m, int B, int T, int H, int W);
+int vda_forward(vda_model* m, const float* x, int B, int T, int H, int W, float* depth, void* workspace,
+                int64_t workspace_bytes, void* stream);
+int vda_destroy(vda_model* m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -131,7 +131,11 @@ class Engine:
             W = sd[wk].detach().to(dev, torch.float32)
             g, beta = f32(nk + ".weight"), f32(nk + ".bias")
             wf = (W * g[None, :]).to(dt).contiguous()
-            return wf, wf.float().sum(1).contiguous(), (W @ beta + f32(bk)).contiguous()
+            # both vectors summed in double and rounded once: independent of the summation order, so the C engine
+            # (csrc/model.cu, host loops) packs the same bits
+            c1 = wf.double().sum(1).float().contiguous()
+            c2 = (W.double() @ beta.double() + f32(bk).double()).float().contiguous()
+            return wf, c1, c2
 
         D = self.D
         pw = sd["pretrained.patch_embed.proj.weight"].detach().to(dev, torch.float32).reshape(D, 588)
