@@ -104,6 +104,22 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] in ("fold", "fol
     fold_set(once=sys.argv[1] == "foldprof")
     sys.exit(0)
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] in ("smallk", "smallkprof"):
+    # the head's small-K GEMMs (K = 256: AI 128 FLOP/B): timed, or one launch each for ncu
+    if sys.argv[1] == "smallkprof":
+        def once(fn, iters=1):
+            fn()
+            torch.cuda.synchronize()
+            return 1.0
+        timeit = once
+    plain("out_conv 1x1 256->256 @74^2", 175232, 256, 256)
+    plain("mm qkv 256->768 @74^2", 175232, 768, 256)
+    plain("mm proj_in 256->256 f32 out", 175232, 256, 256, out_f32=True)
+    plain("mm to_out 256->256 (+res f32)", 175232, 256, 256, out_f32=True, res_f32=True)
+    plain("projects 1024->256", 43808, 256, 1024)
+    conv("RCU conv 256->256 @37^2 +res", 32, 37, 37, 256, 256, res=True)
+    sys.exit(0)
+
 if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("tail", "ln")):
     M = 43840
     if len(sys.argv) > 1 and sys.argv[1] == "prof":     # one launch per shape, for ncu
