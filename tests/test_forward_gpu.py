@@ -168,3 +168,30 @@ def test_infer_video_depth_vs_oracle_resized_multiwindow():
     ref = O.infer_video_depth(sd, frames, "vits", input_size=56)
     mx, p999, mean = O.rel_err(torch.from_numpy(out), torch.from_numpy(ref))
     assert mx <= TOL, f"rel err max {mx:.3e} p99.9 {p999:.3e} mean {mean:.3e}"
+
+
+@pytest.mark.parametrize("reuse", [True, False], ids=["feature-reuse", "per-window"])
+def test_bounded_device_buffers_are_bit_identical_to_unbounded(reuse, monkeypatch):
+    """The long-video driver keeps only a ring of uploaded uint8 frames (4 x 64 + frame 0) and a ring of aligned frames
+    (4 x 22) on the device; a 330-frame video (15 windows: both rings wrap several times) must come out bit-identical to
+    the same call with the rings switched off, and every frame must have been written."""
+    from video_depth_anything_b200 import video_depth as vd
+    m, _ = build_model("vits", 0, torch.bfloat16)
+    n, h0, w0 = 330, 45, 64
+    frames = np.random.default_rng(3).integers(0, 256, (n, h0, w0, 3), dtype=np.uint8)
+    a, _ = m.infer_video_depth(frames, 24, input_size=56, device="cuda", reuse_features=reuse)
+    up_ring = []
+    real_init = vd.FrameUploader.__init__
+
+    def spy(self, *args, **kw):
+        real_init(self, *args, **kw)
+        up_ring.append(self.ring)
+    monkeypatch.setattr(vd.FrameUploader, "__init__", spy)
+    a2, _ = m.infer_video_depth(frames, 24, input_size=56, device="cuda", reuse_features=reuse)
+    assert up_ring == [True]
+    monkeypatch.setattr(vd.FrameUploader, "RING_CHUNKS", 1 << 20)
+    monkeypatch.setattr(vd.WindowAligner, "RING_SEGS", 1 << 20)
+    b, _ = m.infer_video_depth(frames, 24, input_size=56, device="cuda", reuse_features=reuse)
+    assert up_ring == [True, False]
+    assert a.shape == (n, h0, w0) and np.isfinite(a).all() and (a > 0).any(axis=(1, 2)).all()
+    assert np.array_equal(a, a2) and np.array_equal(a, b)

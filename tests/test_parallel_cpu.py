@@ -220,3 +220,67 @@ def test_rank_core_slices_are_disjoint_and_cover():
     assert rank_core_slice(1, 8, list(range(12))) == list(range(12))      # < 2 cores per rank: no pinning
     with pytest.raises(ValueError):
         rank_core_slice(2, 2, cores)
+
+
+# ---- bounded device buffers of the long-video driver (pure index logic in windows.py) -------------------------------
+def test_aligner_ring_every_frame_leaves_once_and_is_never_overwritten_early():
+    """Replay WindowAligner's push / _send bookkeeping on frame ids: each window's 22 new frames and its cross-fade tail are
+    contiguous in the ring, a ring slot is only overwritten after its frame was handed to the D2H pipeline, and the
+    frames leave in order, each exactly once."""
+    from video_depth_anything_b200.windows import INFER_LEN, INTERP_LEN, OVERLAP, aligner_ring_len, aligner_ring_pos
+    seg = INFER_LEN - OVERLAP
+    for n in list(range(1, 300)) + [2048, 2049, 5000]:
+        ring_len = aligner_ring_len(n)
+        assert ring_len % seg == 0 and 2 * seg <= ring_len <= 4 * seg
+        ring, out, sent, filled = [None] * ring_len, [], 0, 0
+
+        def send(upto):
+            nonlocal sent
+            upto = min(upto, n)
+            while upto > sent:
+                r = aligner_ring_pos(sent, ring_len)
+                m = min(upto - sent, ring_len - r)
+                assert ring[r:r + m] == list(range(sent, sent + m))
+                out.extend(range(sent, sent + m))
+                sent += m
+
+        for w in range(-(-n // seg)):
+            if filled == 0:
+                r = aligner_ring_pos(0, ring_len)
+                assert r + INFER_LEN <= ring_len
+                ring[r:r + INFER_LEN] = range(INFER_LEN)
+                filled = INFER_LEN
+            else:
+                rt = aligner_ring_pos(filled - INTERP_LEN, ring_len)
+                assert ring[rt:rt + INTERP_LEN] == list(range(filled - INTERP_LEN, filled))      # tail: contiguous, intact
+                r = aligner_ring_pos(filled, ring_len)
+                assert r % seg == 0 and r + seg <= ring_len
+                assert all(o is None or o < sent for o in ring[r:r + seg])                          # old frames already sent
+                ring[r:r + seg] = range(filled, filled + seg)
+                filled += seg
+            send(filled - INTERP_LEN)
+        send(n)
+        assert out == list(range(n))
+
+
+def test_upload_ring_keeps_every_frame_a_window_reads_resident():
+    """Replay FrameUploader.ensure on frame ids for whole videos and for contiguous rank blocks: when a window runs, every
+    source frame it reads sits in the device slot the index tables point at."""
+    from video_depth_anything_b200.windows import upload_ring_plan, window_source_indices
+    for n, block in ((50, None), (300, None), (700, None), (2048, None), (2048, (40, 60)), (5000, (100, 228))):
+        wins = window_source_indices(n)
+        ids = list(range(len(wins))) if block is None else list(range(*block))
+        needed = sorted({i for k in ids for i in wins[k]})
+        pos = {f: j for j, f in enumerate(needed)}
+        ring, n_slots, slots, chunks = upload_ring_plan(len(needed))
+        assert ring == (len(needed) > 257) and n_slots == (257 if ring else len(needed))
+        assert chunks[0][0] == 0 and chunks[-1][1] == len(needed) and all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
+        dev, uploaded, c = [None] * n_slots, 0, 0
+        for k in ids:
+            while uploaded < pos[max(wins[k])] + 1:
+                lo, hi = chunks[c]
+                d0 = slots[lo]
+                assert slots[lo:hi] == list(range(d0, d0 + hi - lo))            # a chunk lands in consecutive slots
+                dev[d0:d0 + hi - lo] = needed[lo:hi]
+                uploaded, c = hi, c + 1
+            assert all(dev[slots[pos[f]]] == f for f in wins[k])

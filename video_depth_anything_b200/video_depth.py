@@ -25,8 +25,8 @@ import torch.nn as nn
 from . import ops
 from .engine import Engine
 from .synth import ENCODER_DIMS, synth_state_dict
-from .windows import (INFER_LEN, INTERP_LEN, KEYFRAMES, OVERLAP, get_resize_hw, plan_feature_cache,
-                      window_source_indices)
+from .windows import (INFER_LEN, INTERP_LEN, KEYFRAMES, OVERLAP, aligner_ring_len, aligner_ring_pos, get_resize_hw,
+                      plan_feature_cache, upload_ring_plan, window_source_indices)
 
 
 VALIDATION_DTYPE = torch.float16     # operand type of the `fp32=True` path (see _ensure_engine)
@@ -160,7 +160,9 @@ class VideoDepthAnything(nn.Module):
                 return torch.empty(0, INFER_LEN, h0, w0, device=self._device) if raw_only else \
                     (np.empty((0, h0, w0), np.float32), target_fps)
             needed = sorted({i for k in ids for i in wins[k]})
-            up = FrameUploader(frames, needed, self._device)
+            # upload ring: windows in increasing order only; not for the two-phase sharded driver (raw_only), which keeps the
+            # raw stacks of all its windows on the device anyway and whose per-rank share shrinks with the rank count
+            up = FrameUploader(frames, needed, self._device, ring=not raw_only and all(a < b for a, b in zip(ids, ids[1:])))
             # raw stack allocated once: a fresh 34 MB block per window costs a cudaMalloc each (~10 ms at 518x518)
             raws = torch.empty(len(ids), INFER_LEN, h0, w0, dtype=torch.float32, device=self._device) if raw_only else None
             own_aligner = aligner is None and not raw_only
@@ -176,6 +178,7 @@ class VideoDepthAnything(nn.Module):
                     d = cache.window(j)                                      # [32,nh,nw] fp32 (graph-owned buffer)
                 else:
                     x = ops.preprocess_frames(up.dev, idx_all[j], nh, nw).unsqueeze(0)  # [1,32,3,nh,nw]   (:197-201)
+                    up.reads_done(wins[k])
                     d = eng.forward(x)[0]                                    # [32,nh,nw] fp32   (:203-205)
                 if (nh, nw) != (h0, w0):
                     d = ops.bilinear_f32(d, h0, w0, out=raws[j] if raw_only else None)   # video_depth.py:208
@@ -210,10 +213,11 @@ class FeatureCache:
         # each of the 32 window positions].  (A per-window pageable H2D copy synchronises the stream and drains the
         # GPU between windows.)
         table = np.zeros((max(len(windows), 1), 3 * INFER_LEN), dtype=np.int32)
-        self.n_new = []
+        self.n_new, self.missing = [], []
         for j, (missing, slots, positions) in enumerate(plan_feature_cache(windows)):
             n = len(missing)
             self.n_new.append(n)
+            self.missing.append(list(missing))
             table[j, :n] = [up.slot[f] for f in missing]
             table[j, INFER_LEN:INFER_LEN + n] = slots
             table[j, 2 * INFER_LEN:] = positions
@@ -225,6 +229,7 @@ class FeatureCache:
         row = self.table[j]
         if n:
             x = ops.preprocess_frames(self.up.dev, row[:n], self.nh, self.nw)          # [n,3,nh,nw]   (:197-198)
+            self.up.reads_done(self.missing[j])
             taps = eng.encode_frames(x)
             for i in range(4):
                 ops.copy_frames(taps[i].view(n, P, eng.D), None, self.store[i], row[INFER_LEN:INFER_LEN + n], n)
@@ -265,17 +270,27 @@ def _pinned_release(token) -> None:
 
 class FrameUploader:
     """Chunked, asynchronous H2D of the uint8 frames a rank needs (pinned double buffer, copy stream); windows wait
-    only for the chunks that hold their frames, so the upload overlaps the compute of earlier windows."""
+    only for the chunks that hold their frames, so the upload overlaps the compute of earlier windows.
+
+    Device memory is bounded: the first needed frame (source frame 0: slot 0 of every window, video_depth.py:200) keeps a
+    slot of its own, all others go through a ring of RING_CHUNKS x CHUNK frames.  A window reads frame 0 and frames inside
+    a span of 42 consecutive source frames, windows are visited in increasing order and a chunk is only uploaded when the
+    current window needs it, so the chunk a new upload replaces (RING_CHUNKS chunks older) is never read again; the copy
+    waits for the kernels that read it (`reads_done`).  `ring=False` (windows not in increasing order): everything stays."""
 
     CHUNK = 64
+    RING_CHUNKS = 4 if os.environ.get("VDA_VIDEO_RINGS", "1") != "0" else 1 << 20    # VDA_VIDEO_RINGS=0: keep everything
 
-    def __init__(self, frames: np.ndarray, needed: List[int], device):
+    def __init__(self, frames: np.ndarray, needed: List[int], device, ring: bool = True):
         self.frames, self.needed, self.device = frames, needed, device
-        self.slot = {i: j for j, i in enumerate(needed)}
+        self.pos = {i: j for j, i in enumerate(needed)}            # position in upload order
+        self.ring, n_slots, slots, self.chunks = upload_ring_plan(len(needed), self.CHUNK, self.RING_CHUNKS if ring else 1 << 30)
+        self.slot = {i: slots[j] for i, j in self.pos.items()}     # device slot of every needed source frame
         h0, w0 = frames.shape[1:3]
-        self.dev = torch.empty(len(needed), h0, w0, 3, dtype=torch.uint8, device=device)
+        self.dev = torch.empty(n_slots, h0, w0, 3, dtype=torch.uint8, device=device)
         self.stage, self._stage_token = _pinned_acquire(("upload", h0, w0), 2, (self.CHUNK, h0, w0, 3), torch.uint8)
         self.stage_free = [None, None]           # event: staging buffer consumed by its H2D copy
+        self.read_ev = [None] * (self.RING_CHUNKS if self.ring else 0)   # event: the kernels that read the chunk in this ring region are queued
         self.stream = torch.cuda.Stream(device=device)
         # `dev` comes from the caching allocator of the compute stream and may be a block that kernels of an earlier call
         # (still queued on that stream: the raw_only / aligner paths return without synchronising) are yet to read: the
@@ -285,12 +300,16 @@ class FrameUploader:
         self.uploaded = 0                        # number of `needed` entries issued so far
         self.chunk_no = 0
 
+    def _region(self, p: int) -> int:
+        """Ring region of upload position p >= 1."""
+        return ((p - 1) // self.CHUNK) % self.RING_CHUNKS
+
     def ensure(self, max_frame: int) -> None:
         """Issue uploads until source frame `max_frame` is covered, then make the current stream wait for them."""
-        target = self.slot[max_frame] + 1
+        target = self.pos[max_frame] + 1
         last_ev = None
         while self.uploaded < target:
-            lo, hi = self.uploaded, min(self.uploaded + self.CHUNK, len(self.needed))
+            lo, hi = self.chunks[self.chunk_no]
             b = self.chunk_no & 1
             if self.stage_free[b] is not None:
                 self.stage_free[b].synchronize()
@@ -300,8 +319,11 @@ class FrameUploader:
                 np.copyto(st.numpy(), self.frames[src_idx[0]:src_idx[-1] + 1])
             else:
                 np.take(self.frames, src_idx, axis=0, out=st.numpy())
+            d0 = self.slot[src_idx[0]]
             with torch.cuda.stream(self.stream):
-                self.dev[lo:hi].copy_(st, non_blocking=True)
+                if self.ring and lo > 0 and self.read_ev[self._region(lo)] is not None:
+                    self.stream.wait_event(self.read_ev[self._region(lo)])   # readers of the chunk this one replaces
+                self.dev[d0:d0 + hi - lo].copy_(st, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
             self.stage_free[b] = ev
@@ -310,6 +332,17 @@ class FrameUploader:
             self.chunk_no += 1
         if last_ev is not None:
             torch.cuda.current_stream().wait_event(last_ev)
+
+    def reads_done(self, frame_ids: Sequence[int]) -> None:
+        """The kernels that read these source frames from `dev` have been queued on the current stream."""
+        if not self.ring:
+            return
+        regions = {self._region(self.pos[f]) for f in frame_ids if self.pos[f] > 0}
+        if regions:
+            ev = torch.cuda.Event()
+            ev.record()
+            for r in regions:
+                self.read_ev[r] = ev
 
     def close(self) -> None:
         """All uploads have been issued: give the staging buffers back once their H2D copies are done."""
@@ -469,8 +502,10 @@ class HostDrain:
                 self.stage_free[b].set()
                 self.jobs.task_done()
 
-    def send(self, frames: torch.Tensor, host_lo: int) -> None:
-        """Queue device frames [m,h0,w0] (final once the current stream gets here) for host rows [host_lo, host_lo+m)."""
+    def send(self, frames: torch.Tensor, host_lo: int) -> "torch.cuda.Event":
+        """Queue device frames [m,h0,w0] (final once the current stream gets here) for host rows [host_lo, host_lo+m).
+        Returns an event on the copy stream behind the last D2H copy that reads `frames` (a caller that recycles the
+        device memory makes its stream wait for it)."""
         if self.direct:
             self._reg_done.wait()
             if self._reg_ok:                     # DMA straight into the page-locked result rows
@@ -480,9 +515,11 @@ class HostDrain:
                 with torch.cuda.stream(self.copy_stream):
                     self.copy_stream.wait_event(ready)
                     self._host_t[host_lo - lo0:host_lo - lo0 + frames.shape[0]].copy_(frames, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(self.copy_stream)
                 frames.record_stream(self.copy_stream)
                 self.copied_bytes += frames.numel() * 4
-                return
+                return done
         if self.stage is None:
             self.stage, self._stage_token = _pinned_acquire(("drain",) + self._stage_shape[1:], self.STAGES, self._stage_shape,
                                                             torch.float32)
@@ -500,6 +537,7 @@ class HostDrain:
                 ev.record(self.copy_stream)
             self.jobs.put((ev, b, host_lo + off, host_lo + off + part.shape[0]))
             self.batch_no += 1
+        return ev
 
     def finish(self) -> np.ndarray:
         if self.direct:
@@ -526,13 +564,22 @@ def make_blend_weights(device) -> torch.Tensor:
 class WindowAligner:
     """Sequential scale/shift alignment + cross-fade of consecutive windows on the device
     (video_depth.py:216-252, utils/util.py:40-74).  (scale, shift) never leave the GPU; frames that can no longer
-    change (everything but the last 8) are streamed to the host (HostDrain) while the next windows compute."""
+    change (everything but the last 8) are streamed to the host (HostDrain) while the next windows compute.
+
+    Device memory is bounded: the aligned frames live in a ring of RING_SEGS segments of 22 frames (a window adds 22
+    frames and cross-fades into the last 8 of its predecessor; everything older has been handed to the D2H pipeline).
+    Frame a sits at ring position (a + 12) % ring length, which puts the end of window 0 (32 frames) and every later
+    window on segment boundaries, so each window's 22 new frames and its 8-frame cross-fade tail are contiguous; a
+    segment is only overwritten after the D2H copies that read it have completed (events of HostDrain.send)."""
+
+    SEG = INFER_LEN - OVERLAP          # 22 new frames per window
+    RING_SEGS = 4 if os.environ.get("VDA_VIDEO_RINGS", "1") != "0" else 1 << 20
 
     def __init__(self, n_frames: int, h0: int, w0: int, device, mode: str = "affine"):
         self.n, self.h0, self.w0, self.device, self.mode = n_frames, h0, w0, device, mode
-        k = -(-n_frames // (INFER_LEN - OVERLAP))
-        total = k * (INFER_LEN - OVERLAP) + OVERLAP
-        self.out = torch.empty(total, h0, w0, dtype=torch.float32, device=device)
+        self.ring_len = aligner_ring_len(n_frames, self.RING_SEGS)
+        self.out = torch.empty(self.ring_len, h0, w0, dtype=torch.float32, device=device)
+        self.seg_ev = [None] * (self.ring_len // self.SEG)               # last D2H copy that reads the segment
         self.filled = 0
         self.ref = None                      # [2,h0,w0]: (ref_align[0], ref_align[1])
         self.ss = torch.tensor([1.0, 0.0], dtype=torch.float32, device=device)
@@ -541,31 +588,47 @@ class WindowAligner:
         self.drain = HostDrain(np.empty((n_frames, h0, w0), dtype=np.float32), device)
         self.sent = 0                        # frames already handed to the D2H pipeline
 
+    def _pos(self, a: int) -> int:
+        return aligner_ring_pos(a, self.ring_len)
+
+    def _claim(self, r: int, m: int) -> torch.Tensor:
+        """Ring frames [r, r+m) for writing: the D2H copies of what they held must have completed."""
+        for g in range(r // self.SEG, (r + m - 1) // self.SEG + 1):
+            if self.seg_ev[g] is not None:
+                torch.cuda.current_stream().wait_event(self.seg_ev[g])
+                self.seg_ev[g] = None
+        return self.out[r:r + m]
+
     def _send(self, upto: int) -> None:
         """Stream frames [sent, upto) (final values) to the host."""
         upto = min(upto, self.n)
-        if upto > self.sent:
-            self.drain.send(self.out[self.sent:upto], self.sent)
-            self.sent = upto
+        while upto > self.sent:
+            r = self._pos(self.sent)
+            m = min(upto - self.sent, self.ring_len - r)                  # (split where the ring wraps)
+            ev = self.drain.send(self.out[r:r + m], self.sent)
+            for g in range(r // self.SEG, (r + m - 1) // self.SEG + 1):
+                self.seg_ev[g] = ev
+            self.sent += m
 
     def push(self, d: torch.Tensor) -> None:
         """d: raw depths of the next window, fp32 [32,h0,w0]."""
         d = d.contiguous()
         align_len = OVERLAP - INTERP_LEN                                  # 2; kf_align_list = [0, 12]
         if self.filled == 0:
-            self.out[:INFER_LEN].copy_(d)                                 # window 0 copied unclamped (:222-225)
+            self._claim(self._pos(0), INFER_LEN).copy_(d)                 # window 0 copied unclamped (:222-225)
             self.ref = torch.stack([d[KEYFRAMES[0]], d[KEYFRAMES[1]]])
             self.filled = INFER_LEN
         else:
             if self.mode == "affine":
                 ops.lsq_scale_shift(d[:align_len], self.ref, self.ss, self.scratch)      # :227-232
-            tail = self.out[self.filled - INTERP_LEN:self.filled]
+            rt = self._pos(self.filled - INTERP_LEN)                      # the last 8 frames of the previous segment
+            tail = self.out[rt:rt + INTERP_LEN]
             ops.affine_clamp_blend(d[align_len:OVERLAP], self.ss, tail, prev=tail, blend_w=self.blend_w)   # :234-239
-            new = self.out[self.filled:self.filled + INFER_LEN - OVERLAP]
+            new = self._claim(self._pos(self.filled), self.SEG)
             ops.affine_clamp_blend(d[OVERLAP:], self.ss, new)                                              # :241-244
             ref1 = self.ref[1:2]
             ops.affine_clamp_blend(d[KEYFRAMES[1]:KEYFRAMES[1] + 1], self.ss, ref1)                       # :246-250
-            self.filled += INFER_LEN - OVERLAP
+            self.filled += self.SEG
         self._send(self.filled - INTERP_LEN)          # the last 8 frames are still cross-faded with the next window
 
     def result(self) -> np.ndarray:

@@ -97,3 +97,36 @@ def plan_feature_cache(windows, n_slots: int = INFER_LEN):
         where.update(zip(missing, slots))
         plan.append((missing, slots, [where[f] for f in src]))
     return plan
+
+
+# ------------------------------------------------------------------------------------------------
+# bounded device buffers of the long-video driver (pure index logic; the device side is video_depth.FrameUploader /
+# video_depth.WindowAligner, the property tests are tests/test_parallel_cpu.py::test_*_ring_*)
+# ------------------------------------------------------------------------------------------------
+def aligner_ring_len(n_frames: int, ring_segs: int = 4) -> int:
+    """Length of the WindowAligner's ring of aligned frames: `ring_segs` segments of 22 frames, fewer for short videos
+    (never less than the 44 frames window 0 needs behind the 12-frame shift)."""
+    seg = INFER_LEN - OVERLAP
+    k = -(-n_frames // seg)
+    total = k * seg + OVERLAP
+    return seg * min(ring_segs, (total + seg - OVERLAP) // seg)
+
+
+def aligner_ring_pos(a: int, ring_len: int) -> int:
+    """Ring position of aligned frame `a`: shifted by 12 so that window 0 (32 frames) ends, and every later window's 22
+    new frames start, on a segment boundary -- a window's new frames and its 8-frame cross-fade tail never wrap."""
+    return (a + INFER_LEN - 2 * OVERLAP) % ring_len
+
+
+def upload_ring_plan(n_needed: int, chunk: int = 64, ring_chunks: int = 4):
+    """Device slots and upload chunks of the FrameUploader for `n_needed` frames in upload order.  Returns
+    (ring, n_slots, slot_of_position, chunks) with chunks = [(lo, hi)] in upload order.  With the ring on, position 0 (source
+    frame 0, read by every window) owns slot 0 and is uploaded alone; positions >= 1 share `ring_chunks * chunk` slots and
+    are uploaded in chunks aligned to the ring regions, so chunk m replaces chunk m - ring_chunks."""
+    cap = chunk * ring_chunks
+    ring = n_needed > 1 + cap
+    if not ring:
+        return False, n_needed, list(range(n_needed)), [(lo, min(lo + chunk, n_needed)) for lo in range(0, n_needed, chunk)]
+    slots = [0] + [1 + (j - 1) % cap for j in range(1, n_needed)]
+    chunks = [(0, 1)] + [(lo, min(lo + chunk, n_needed)) for lo in range(1, n_needed, chunk)]
+    return True, 1 + cap, slots, chunks
