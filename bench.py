@@ -371,6 +371,10 @@ def main():
         # warm-up on the same video: graphs for the 32/22-frame encodes, allocator blocks, pinned staging / NCCL buffers of
         # the sizes the timed call uses (a short warm-up video left an unexplained ~25 ms in the 8-GPU exchange)
         infer_video_depth_sharded(model, frames, 24, device=dev)
+        # the sharded driver releases the page lock of the warm-up call's result half a second after that call, in a
+        # background thread (cudaHostUnregister holds the context lock for tens of ms per 100 MB): let it finish outside the
+        # timed call instead of 0.5 s into it (seen once in four 2-GPU runs: 2.59 s instead of 2.01 s)
+        time.sleep(1.0 if world > 1 else 0.0)
         barrier()
         l0 = ops.LAUNCHES
         t0 = time.perf_counter()
