@@ -130,7 +130,6 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmW, const TailParams p) {
   } else if (warp <= NPROD) {
     // ================================ producers: upsampled halo tile =====================
     const int ptid = threadIdx.x - 32;                       // 0 .. 32*NPROD-1
-    constexpr int units = HH * HW_ * KC;
     const T* in = reinterpret_cast<const T*>(p.in);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -142,11 +141,14 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmW, const TailParams p) {
       const T* src = in + static_cast<long long>(img) * p.IH * p.IW * CC;
       mbar_wait(&a_empty[buf], ph ^ 1u);
       const uint32_t abase = smem_base + offA + buf * halo_bytes;
-      // UB units per thread are in flight at once: all 4*UB neighbour loads are issued before any arithmetic
+      // A unit is one halo pixel x 16 channels (two 8-channel chunks): the pixel's coordinates, interpolation weights and
+      // tap offsets are computed once per 16 channels (they were half of a unit's instructions when a unit was 8
+      // channels).  UB units per thread are in flight at once: all 8*UB neighbour loads are issued before any arithmetic
       // (one L1/L2 round trip per batch instead of one per unit)
-      constexpr int UB = 4;
-      for (int u0 = ptid; u0 < units; u0 += 32 * NPROD * UB) {
-        uint4 a[UB][4];
+      constexpr int UB = 2, KC2 = KC / 2;
+      constexpr int units2 = HH * HW_ * KC2;
+      for (int u0 = ptid; u0 < units2; u0 += 32 * NPROD * UB) {
+        uint4 a[UB][4][2];
         float wy[UB], wx[UB];
         uint32_t dst[UB];
         int state[UB];                                         // 0: no unit, 1: zero (padding), 2: interpolate
@@ -154,9 +156,10 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmW, const TailParams p) {
         for (int b = 0; b < UB; ++b) {
           const int u = u0 + b * 32 * NPROD;
           state[b] = 0;
-          if (u < units) {
-            const int kc = u % KC;
-            const int px = u / KC;
+          wy[b] = wx[b] = 0.f;
+          if (u < units2) {
+            const int kc = 2 * (u % KC2);
+            const int px = u / KC2;
             const int hy = px / HW_, hx = px - hy * HW_;
             const int Y = Y0 + hy, X = X0 + hx;
             dst[b] = abase + hy * row_stride + kc * chunk_stride + hx * 16;
@@ -169,37 +172,47 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tmW, const TailParams p) {
               wy[b] = fy - y0;
               wx[b] = fx - x0;
               const T* bp = src + kc * 8;
-              a[b][0] = *reinterpret_cast<const uint4*>(bp + (y0 * p.IW + x0) * CC);
-              a[b][1] = *reinterpret_cast<const uint4*>(bp + (y0 * p.IW + x1) * CC);
-              a[b][2] = *reinterpret_cast<const uint4*>(bp + (y1 * p.IW + x0) * CC);
-              a[b][3] = *reinterpret_cast<const uint4*>(bp + (y1 * p.IW + x1) * CC);
+              const T* t00 = bp + (y0 * p.IW + x0) * CC;
+              const T* t01 = bp + (y0 * p.IW + x1) * CC;
+              const T* t10 = bp + (y1 * p.IW + x0) * CC;
+              const T* t11 = bp + (y1 * p.IW + x1) * CC;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                a[b][0][h] = *reinterpret_cast<const uint4*>(t00 + 8 * h);
+                a[b][1][h] = *reinterpret_cast<const uint4*>(t01 + 8 * h);
+                a[b][2][h] = *reinterpret_cast<const uint4*>(t10 + 8 * h);
+                a[b][3][h] = *reinterpret_cast<const uint4*>(t11 + 8 * h);
+              }
             }
           }
         }
 #pragma unroll
         for (int b = 0; b < UB; ++b) {
           if (state[b] == 0) continue;
-          uint4 res = make_uint4(0u, 0u, 0u, 0u);
-          if (state[b] == 2) {
-            const float ly = wy[b], lx = wx[b];
-            const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-            const uint32_t p00[4] = {a[b][0].x, a[b][0].y, a[b][0].z, a[b][0].w};
-            const uint32_t p01[4] = {a[b][1].x, a[b][1].y, a[b][1].z, a[b][1].w};
-            const uint32_t p10[4] = {a[b][2].x, a[b][2].y, a[b][2].z, a[b][2].w};
-            const uint32_t p11[4] = {a[b][3].x, a[b][3].y, a[b][3].z, a[b][3].w};
-            uint32_t r[4];
+          const float ly = wy[b], lx = wx[b];
+          const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 f00 = H16<T>::unpack2(p00[i]), f01 = H16<T>::unpack2(p01[i]);
-              const float2 f10 = H16<T>::unpack2(p10[i]), f11 = H16<T>::unpack2(p11[i]);
-              r[i] = H16<T>::pack2(w00 * f00.x + w01 * f01.x + w10 * f10.x + w11 * f11.x,
-                                   w00 * f00.y + w01 * f01.y + w10 * f10.y + w11 * f11.y);
+          for (int h = 0; h < 2; ++h) {
+            uint4 res = make_uint4(0u, 0u, 0u, 0u);
+            if (state[b] == 2) {
+              const uint32_t p00[4] = {a[b][0][h].x, a[b][0][h].y, a[b][0][h].z, a[b][0][h].w};
+              const uint32_t p01[4] = {a[b][1][h].x, a[b][1][h].y, a[b][1][h].z, a[b][1][h].w};
+              const uint32_t p10[4] = {a[b][2][h].x, a[b][2][h].y, a[b][2][h].z, a[b][2][h].w};
+              const uint32_t p11[4] = {a[b][3][h].x, a[b][3][h].y, a[b][3][h].z, a[b][3][h].w};
+              uint32_t r[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f00 = H16<T>::unpack2(p00[i]), f01 = H16<T>::unpack2(p01[i]);
+                const float2 f10 = H16<T>::unpack2(p10[i]), f11 = H16<T>::unpack2(p11[i]);
+                r[i] = H16<T>::pack2(w00 * f00.x + w01 * f01.x + w10 * f10.x + w11 * f11.x,
+                                     w00 * f00.y + w01 * f01.y + w10 * f10.y + w11 * f11.y);
+              }
+              res = make_uint4(r[0], r[1], r[2], r[3]);
             }
-            res = make_uint4(r[0], r[1], r[2], r[3]);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst[b] + h * chunk_stride), "r"(res.x), "r"(res.y),
+                         "r"(res.z), "r"(res.w)
+                         : "memory");
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst[b]), "r"(res.x), "r"(res.y), "r"(res.z),
-                       "r"(res.w)
-                       : "memory");
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA
